@@ -1,0 +1,30 @@
+"""bayes_kit_b200 -- B200-native (sm_100a) drop-in for bayes-kit's data-parallel
+sampling hot path: many independent chains / particles advanced in lockstep by
+hand-written CUDA kernels behind bayes-kit's own API surface.
+
+Same names as ``bayes_kit/__init__.py:1-30``; models are device plugins
+(``bayes_kit_b200.models``), chain state lives in torch CUDA tensors, and every
+kernel is reached through the C ABI of ``include/bk.h`` (ctypes).  There is no
+CPU fallback.
+"""
+from . import dist, models
+from .autocorr import autocorr
+from .drghmc import DrGhmcDiag
+from .ensemble import Stretcher
+from .ess import ess, ess_imse, ess_ipse
+from .hmc import HMCDiag
+from .iat import iat, iat_imse, iat_ipse
+from .mala import MALA
+from .metropolis import (GaussianRW, Metropolis, MetropolisHastings, metropolis_accept_test,
+                         metropolis_hastings_accept_test)
+from .models import DensePrecGauss, DiagGauss, GaussPriorLik, HierLogReg, IsoGauss, StdNormal
+from .rhat import chain_moments, rhat
+from .smc import TemperedLikelihoodSMC, metropolis_kernel
+
+__all__ = [
+    "DrGhmcDiag", "HMCDiag", "MALA", "Metropolis", "MetropolisHastings", "TemperedLikelihoodSMC",
+    "Stretcher", "ess", "ess_imse", "ess_ipse", "iat", "iat_imse", "iat_ipse", "rhat", "autocorr",
+    # device-side additions
+    "GaussianRW", "metropolis_kernel", "models", "dist", "IsoGauss", "StdNormal", "DiagGauss",
+    "DensePrecGauss", "GaussPriorLik", "HierLogReg", "chain_moments",
+]

@@ -1,0 +1,168 @@
+// Fused samplers for separable (iso / diagonal Gaussian) model plugins:
+// one launch = n_draws x C chains of HMCDiag / MALA / random-walk Metropolis.
+// theta, rho and the gradient live in registers across all L leapfrog steps;
+// momentum comes from in-kernel Philox (or an injected stream), the
+// Hamiltonian, the per-chain reductions (group shuffles) and the Metropolis
+// test are evaluated in-kernel; only the draw (+ logp, accept flag) goes to HBM.
+//
+// Reference semantics: hmc.py:36-63, mala.py:40-79, metropolis.py:12-135.
+#include "sampler_sep.h"
+
+namespace bk {
+
+template <typename T, int G, int J, int MK, int ALGO>
+__global__ void __launch_bounds__(128) k_sep_sampler(SepArgs<T> a) {
+    using A = Ar<T>;
+    constexpr int NE = 4 * J;
+    // Lanes past the last chain shadow chain C-1 (they must stay in the warp
+    // for the full-mask group shuffles) and skip every store.
+    const int64_t chain_raw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool active = chain_raw < a.C;
+    const int64_t chain = active ? chain_raw : a.C - 1;
+    Lanes<T, G, J> ln;
+    ln.lane = threadIdx.x % G;
+    ln.D = a.D;
+    ln.vec = a.vec != 0;
+    SepGauss<T, G, J, MK> md;
+    md.init(a.model, ln);
+
+    T th[NE];
+    ln.load(a.theta + chain * (int64_t)a.D, th, T(0));
+    T lp = md.logp(th);  // cached log p(theta) (mala.py:31, metropolis.py:99)
+
+    for (int64_t t = 0; t < a.n_draws; ++t) {
+        T z[NE];
+        ln.normals(a.rng, a.C, chain, t, z);
+        const T logu = log_u(ln.uniform(a.rng, a.C, chain, t, 0));
+        bool acc;
+        T out_lp;
+        if constexpr (ALGO == ALGO_HMC) {
+            // hmc.py:55-63
+            const T h0 = A::sub(md.logp(th), md.kinetic(z));
+            T q[NE];
+#pragma unroll
+            for (int k = 0; k < NE; ++k) {  // backward half kick (hmc.py:46)
+                q[k] = th[k];
+                z[k] = A::sub(z[k], A::mul(a.half_eps, md.mgrad(th, k)));
+            }
+            for (int s = 0; s < a.L; ++s) {  // hmc.py:47-50
+#pragma unroll
+                for (int k = 0; k < NE; ++k) {
+                    z[k] = A::add(z[k], A::mul(a.eps, md.mgrad(q, k)));
+                    q[k] = A::add(q[k], A::mul(a.eps, z[k]));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NE; ++k)  // forward half kick (hmc.py:52)
+                z[k] = A::add(z[k], A::mul(a.half_eps, md.mgrad(q, k)));
+            const T h1 = A::sub(md.logp(q), md.kinetic(z));
+            acc = logu < A::sub(h1, h0);
+            if (acc) {
+#pragma unroll
+                for (int k = 0; k < NE; ++k) th[k] = q[k];
+            }
+            out_lp = acc ? h1 : h0;
+        } else if constexpr (ALGO == ALGO_MALA) {
+            // mala.py:40-66
+            T q[NE];
+#pragma unroll
+            for (int k = 0; k < NE; ++k)
+                q[k] = A::add(A::add(th[k], A::mul(a.eps, md.grad(th, k))), A::mul(a.sd, z[k]));
+            const T lp_p = md.logp(q);
+            T sf = T(0), sr = T(0);
+#pragma unroll
+            for (int k = 0; k < NE; ++k) {
+                if (ln.valid(k)) {
+                    T df = A::sub(A::sub(q[k], th[k]), A::mul(a.eps, md.grad(th, k)));
+                    T dr = A::sub(A::sub(th[k], q[k]), A::mul(a.eps, md.grad(q, k)));
+                    sf = A::add(sf, A::mul(df, df));
+                    sr = A::add(sr, A::mul(dr, dr));
+                }
+            }
+            const T fwd = A::mul(a.coef, group_sum<G>(sf));
+            const T rev = A::mul(a.coef, group_sum<G>(sr));
+            acc = logu < A::add(A::sub(lp_p, lp), A::sub(rev, fwd));
+            if (acc) {
+#pragma unroll
+                for (int k = 0; k < NE; ++k) th[k] = q[k];
+                lp = lp_p;
+            }
+            out_lp = lp;
+        } else {
+            // metropolis.py:107-135 with proposal normal(loc=theta, scale)
+            T q[NE];
+#pragma unroll
+            for (int k = 0; k < NE; ++k) q[k] = A::add(th[k], A::mul(a.scale, z[k]));
+            const T lp_p = md.logp(q);
+            T ratio = A::sub(lp_p, lp);
+            if (a.hastings) {
+                T sf = T(0), sr = T(0);
+#pragma unroll
+                for (int k = 0; k < NE; ++k) {
+                    T df = A::sub(q[k], th[k]), dr = A::sub(th[k], q[k]);
+                    sf = A::add(sf, A::mul(df, df));
+                    sr = A::add(sr, A::mul(dr, dr));
+                }
+                const T fwd = A::mul(T(-0.5), group_sum<G>(sf)) / a.s2;
+                const T rev = A::mul(T(-0.5), group_sum<G>(sr)) / a.s2;
+                ratio = A::add(ratio, A::sub(rev, fwd));
+            }
+            acc = logu < ratio;
+            if (acc) {
+#pragma unroll
+                for (int k = 0; k < NE; ++k) th[k] = q[k];
+                lp = lp_p;
+            }
+            out_lp = lp;
+        }
+        if (a.draws && active) ln.store(a.draws + (t * a.C + chain) * (int64_t)a.D, th);
+        if (ln.lane == 0 && active) {
+            if (a.logp) a.logp[t * a.C + chain] = out_lp;
+            if (a.accept) a.accept[t * a.C + chain] = acc ? 1 : 0;
+        }
+    }
+    if (active) ln.store(a.theta + chain * (int64_t)a.D, th);
+}
+
+template <typename T, int G, int J, int MK>
+static int launch_gj(const SepArgs<T>& a, cudaStream_t st) {
+    const int threads = 128;
+    const int64_t chains_per_block = threads / G;
+    const int64_t blocks = (a.C + chains_per_block - 1) / chains_per_block;
+    if (blocks == 0) return BK_OK;
+    prof_begin(BK_PROF_SAMPLER, st);
+    switch (a.algo) {
+        case ALGO_HMC: k_sep_sampler<T, G, J, MK, ALGO_HMC><<<(unsigned)blocks, threads, 0, st>>>(a); break;
+        case ALGO_MALA: k_sep_sampler<T, G, J, MK, ALGO_MALA><<<(unsigned)blocks, threads, 0, st>>>(a); break;
+        case ALGO_MHRW: k_sep_sampler<T, G, J, MK, ALGO_MHRW><<<(unsigned)blocks, threads, 0, st>>>(a); break;
+        default: set_error("unknown fused algo %d", a.algo); return BK_E_INVALID;
+    }
+    prof_end(BK_PROF_SAMPLER, st);
+    BK_LAUNCH_CHECK();
+    return BK_OK;
+}
+
+template <typename T, int MK>
+static int launch_mk(const SepArgs<T>& a, cudaStream_t st) {
+    const int D = a.D;
+    if (D <= 4) return launch_gj<T, 1, 1, MK>(a, st);
+    if (D <= 16) return launch_gj<T, 4, 1, MK>(a, st);
+    if (D <= 32) return launch_gj<T, 8, 1, MK>(a, st);
+    if (D <= 64) return launch_gj<T, 16, 1, MK>(a, st);
+    if (D <= 128) return launch_gj<T, 32, 1, MK>(a, st);
+    if (D <= 256) return launch_gj<T, 32, 2, MK>(a, st);
+    if (D <= 512) return launch_gj<T, 32, 4, MK>(a, st);
+    set_error("fused separable sampler supports D <= %d (got %d)", SEP_MAX_D, D);
+    return BK_E_UNSUPPORTED;
+}
+
+template <typename T>
+int launch_sep_sampler(const SepArgs<T>& a, cudaStream_t st) {
+    const bool iso = a.model.mu == nullptr && a.model.prec == nullptr && a.model.metric == nullptr;
+    return iso ? launch_mk<T, MK_ISO>(a, st) : launch_mk<T, MK_DIAG>(a, st);
+}
+
+template int launch_sep_sampler<float>(const SepArgs<float>&, cudaStream_t);
+template int launch_sep_sampler<double>(const SepArgs<double>&, cudaStream_t);
+
+}  // namespace bk

@@ -1,0 +1,174 @@
+// Register-resident chain state for the fused "separable model" samplers.
+//
+// A chain is owned by a group of G consecutive lanes (G = 1..32); each lane
+// keeps NE = 4*J elements of every per-dimension vector in registers:
+// element e = 4*(lane + G*j) + i  (j < J, i < 4), i.e. float4-vectorised,
+// lane-strided -> every global access of a group is one contiguous segment.
+// theta / rho never touch HBM between the L leapfrog steps of a draw.
+#pragma once
+#include "common.cuh"
+
+namespace bk {
+
+enum { MK_ISO = 0, MK_DIAG = 1 };
+
+template <typename T>
+struct SepModel {
+    const T* mu;      // [D] or NULL
+    const T* prec;    // [D] or NULL (-> prec_scalar)
+    T prec_scalar;
+    const T* metric;  // [D] or NULL (identity)
+};
+
+template <typename T, int G, int J>
+struct Lanes {
+    static constexpr int NE = 4 * J;
+    int lane;   // lane within group
+    int D;
+    bool vec;
+    __device__ __forceinline__ int elem(int k) const { return 4 * (lane + G * (k >> 2)) + (k & 3); }
+    __device__ __forceinline__ bool valid(int k) const { return elem(k) < D; }
+
+    __device__ __forceinline__ void load(const T* row, T (&v)[NE], T fill) const {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            int e0 = 4 * (lane + G * j);
+            if (vec && e0 + 3 < D) {
+                if constexpr (sizeof(T) == 4) {
+                    float4 t = *reinterpret_cast<const float4*>(row + e0);
+                    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+                } else {
+                    double2 a = *reinterpret_cast<const double2*>(row + e0);
+                    double2 b = *reinterpret_cast<const double2*>(row + e0 + 2);
+                    v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = b.x; v[4 * j + 3] = b.y;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[4 * j + i] = (e0 + i < D) ? row[e0 + i] : fill;
+            }
+        }
+    }
+    __device__ __forceinline__ void store(T* row, const T (&v)[NE]) const {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            int e0 = 4 * (lane + G * j);
+            if (vec && e0 + 3 < D) {
+                if constexpr (sizeof(T) == 4) {
+                    *reinterpret_cast<float4*>(row + e0) =
+                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                } else {
+                    *reinterpret_cast<double2*>(row + e0) = make_double2(v[4 * j], v[4 * j + 1]);
+                    *reinterpret_cast<double2*>(row + e0 + 2) = make_double2(v[4 * j + 2], v[4 * j + 3]);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (e0 + i < D) row[e0 + i] = v[4 * j + i];
+            }
+        }
+    }
+    // standard normals for (chain, draw); invalid slots are 0
+    __device__ __forceinline__ void normals(const bk_rng& rng, int64_t C, int64_t chain, int64_t t,
+                                            T (&z)[NE]) const {
+        if (rng.mode == BK_RNG_INJECTED) {
+            load(reinterpret_cast<const T*>(rng.normals) + (t * C + chain) * (int64_t)D, z, T(0));
+        } else {
+            uint32_t gc = (uint32_t)(rng.chain_offset + (uint64_t)chain);
+            uint32_t gd = (uint32_t)(rng.draw_offset + (uint64_t)t);
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                int blk = lane + G * j;
+                T q[4];
+                philox_normal4<T>(rng.seed, (uint32_t)blk, gc, gd, q);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) z[4 * j + i] = (4 * blk + i < D) ? q[i] : T(0);
+            }
+        }
+    }
+    __device__ __forceinline__ T uniform(const bk_rng& rng, int64_t C, int64_t chain, int64_t t,
+                                         int k) const {
+        if (rng.mode == BK_RNG_INJECTED)
+            return reinterpret_cast<const T*>(rng.uniforms)[(t * C + chain) * rng.n_uniform + k];
+        return philox_uniform<T>(rng.seed, (uint32_t)k, (uint32_t)(rng.chain_offset + (uint64_t)chain),
+                                 (uint32_t)(rng.draw_offset + (uint64_t)t));
+    }
+};
+
+// log(u) with numpy semantics for u == 0 (-inf: always accepts)
+template <typename T>
+__device__ __forceinline__ T log_u(T u) {
+    return u > T(0) ? Ar<T>::log_(u) : neg_inf<T>();
+}
+
+// Per-lane view of a diagonal Gaussian (MK_ISO keeps nothing per element).
+template <typename T, int G, int J, int MK>
+struct SepGauss {
+    using A = Ar<T>;
+    static constexpr int NE = 4 * J;
+    T pr[MK == MK_DIAG ? NE : 1];
+    T mu[MK == MK_DIAG ? NE : 1];
+    T me[MK == MK_DIAG ? NE : 1];
+    T prec_scalar;
+
+    __device__ __forceinline__ void init(const SepModel<T>& m, const Lanes<T, G, J>& ln) {
+        prec_scalar = m.prec_scalar;
+        if constexpr (MK == MK_DIAG) {
+            if (m.prec) ln.load(m.prec, pr, T(0));
+            else {
+#pragma unroll
+                for (int k = 0; k < NE; ++k) pr[k] = ln.valid(k) ? m.prec_scalar : T(0);
+            }
+            if (m.mu) ln.load(m.mu, mu, T(0));
+            else {
+#pragma unroll
+                for (int k = 0; k < NE; ++k) mu[k] = T(0);
+            }
+            if (m.metric) ln.load(m.metric, me, T(0));
+            else {
+#pragma unroll
+                for (int k = 0; k < NE; ++k) me[k] = T(1);
+            }
+        }
+    }
+    // gradient of log p at x (element k)
+    __device__ __forceinline__ T grad(const T (&x)[NE], int k) const {
+        if constexpr (MK == MK_ISO) return -A::mul(prec_scalar, x[k]);
+        else return -A::mul(pr[k], A::sub(x[k], mu[k]));
+    }
+    // metric * gradient
+    __device__ __forceinline__ T mgrad(const T (&x)[NE], int k) const {
+        if constexpr (MK == MK_ISO) return grad(x, k);
+        else return A::mul(me[k], grad(x, k));
+    }
+    // log density (group-reduced; identical in every lane of the group)
+    __device__ __forceinline__ T logp(const T (&x)[NE]) const {
+        T s = T(0);
+        if constexpr (MK == MK_ISO) {
+#pragma unroll
+            for (int k = 0; k < NE; ++k) s = A::add(s, A::mul(x[k], x[k]));
+            s = group_sum<G>(s);
+            return A::mul(T(-0.5), A::mul(prec_scalar, s));
+        } else {
+#pragma unroll
+            for (int k = 0; k < NE; ++k) {
+                T d = A::sub(x[k], mu[k]);
+                s = A::add(s, A::mul(d, A::mul(pr[k], d)));
+            }
+            s = group_sum<G>(s);
+            return A::mul(T(-0.5), s);
+        }
+    }
+    // 0.5 * rho . (metric * rho)
+    __device__ __forceinline__ T kinetic(const T (&r)[NE]) const {
+        T s = T(0);
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            if constexpr (MK == MK_ISO) s = A::add(s, A::mul(r[k], r[k]));
+            else s = A::add(s, A::mul(r[k], A::mul(me[k], r[k])));
+        }
+        s = group_sum<G>(s);
+        return A::mul(T(0.5), s);
+    }
+};
+
+}  // namespace bk

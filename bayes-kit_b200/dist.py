@@ -1,0 +1,61 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL on GPUs,
+gloo in the CPU tests).  Sampling is communication-free (chains shard
+contiguously, Philox is keyed by the GLOBAL chain id); collectives appear only
+at the naturally global steps: SMC normaliser / resampling and cross-chain
+R-hat moments.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def rank_world(group=None) -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of n items for `rank`; the first n % world
+    ranks get one extra item."""
+    base, extra = divmod(int(n), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_sizes(n: int, world: int):
+    return [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
+
+
+def all_gather_cat(t: torch.Tensor, group=None) -> torch.Tensor:
+    """Concatenate every rank's tensor along dim 0 (ragged first dim allowed)."""
+    rank, world = rank_world(group)
+    if world == 1:
+        return t
+    n_local = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(sizes, n_local, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    mx = max(sizes)
+    pad = t
+    if t.shape[0] < mx:
+        pad = torch.cat([t, t.new_zeros((mx - t.shape[0],) + tuple(t.shape[1:]))])
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad.contiguous(), group=group)
+    return torch.cat([b[:s] for b, s in zip(bufs, sizes)]).contiguous()
+
+
+def all_reduce_logsumexp(local_max: torch.Tensor, local_sumexp: torch.Tensor, group=None):
+    """Global log-normaliser pieces from per-rank (max, sum exp(x - max)):
+    returns (gmax, sum exp(x - gmax)) -- 2 scalars on the wire."""
+    rank, world = rank_world(group)
+    if world == 1:
+        return local_max, local_sumexp
+    gmax = local_max.clone()
+    dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
+    s = local_sumexp * torch.exp(local_max - gmax)
+    dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+    return gmax, s

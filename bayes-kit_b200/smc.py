@@ -1,0 +1,154 @@
+"""TemperedLikelihoodSMC (reference: bayes_kit/smc.py).
+
+All M particles move, reweight and resample on device, one temperature per
+``transition(n)``: a fused RW-Metropolis move + log-weight kernel, a block-scan
+CDF + binary-search resampler and a row gather.  Particles shard across ranks;
+the only communication is the naturally global resampling step (all-gather of
+log-weights and particles over NCCL), see dist.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterator, Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import dist as D_
+from ._util import Workspace, make_rng, ptr, resolve_seed, stream_ptr, to_dev
+from .models import GaussPriorLik, require_plugin
+
+
+class RWMetropolisKernel:
+    """Device descriptor returned by ``metropolis_kernel(scale)``: one
+    random-walk Metropolis move ``theta* = normal(loc=theta, scale)`` accepted
+    iff ``log(u) < lp(theta*) - lp(theta)`` (smc.py:79-89)."""
+
+    def __init__(self, scale: float):
+        self.scale = float(scale)
+        if not self.scale > 0:
+            raise ValueError(f"scale must be positive, got {scale}")
+
+
+def metropolis_kernel(scale: float) -> RWMetropolisKernel:
+    return RWMetropolisKernel(scale)
+
+
+class TemperedLikelihoodSMC:
+    """``TemperedLikelihoodSMC(model, M, N, sample_initial, kernel)`` (smc.py:13-27).
+
+    * ``model``: a ``GaussPriorLik`` plugin (``log_prior`` / ``log_likelihood``).
+    * ``sample_initial``: the reference's callable ``m -> theta0[m]`` (evaluated
+      once per particle on the host, as smc.py:23 does), or directly an [M, D]
+      array / tensor.
+    * ``kernel``: ``metropolis_kernel(scale)``.
+    * ``resample``: ``"multinomial"`` (reference semantics: no max-shift, legacy
+      ``np.random.choice`` indices) or ``"systematic"`` (log-sum-exp normalised,
+      stratified points; north_star item 2).
+    With torch.distributed initialised, M is the GLOBAL particle count and each
+    rank owns a contiguous slice.
+    """
+
+    def __init__(self, model, M: int, N: int, sample_initial, kernel, *, resample: str = "multinomial",
+                 seed=None, group=None):
+        self._model = require_plugin(model)
+        if not isinstance(self._model, GaussPriorLik):
+            raise TypeError("TemperedLikelihoodSMC needs a model plugin with log_prior/log_likelihood "
+                            "(bayes_kit_b200.models.GaussPriorLik)")
+        if not isinstance(kernel, RWMetropolisKernel):
+            raise TypeError("kernel must be bayes_kit_b200.metropolis_kernel(scale): arbitrary Python "
+                            "kernels cannot run per particle on the GPU and there is no CPU fallback")
+        if resample not in ("multinomial", "systematic"):
+            raise ValueError("resample must be 'multinomial' or 'systematic'")
+        self.M, self.N = int(M), int(N)
+        self.kernel = kernel
+        self.resample = resample
+        self.device, self.dtype = self._model.device, self._model.dtype
+        self._seed = resolve_seed(seed)
+        self._group = group
+        self._rank, self._world = D_.rank_world(group)
+        self._lo, self._hi = D_.shard_range(self.M, self._rank, self._world)
+        if callable(sample_initial):
+            th = np.array([np.asarray(sample_initial(m), dtype=np.float64)
+                           for m in range(self._lo, self._hi)])
+            th = th.reshape(self._hi - self._lo, -1)
+        else:
+            th = sample_initial
+            if th.shape[0] == self.M and self._world > 1:
+                th = th[self._lo:self._hi]
+        self.thetas = to_dev(th, self.dtype, self.device).clone()
+        self.D = self.thetas.shape[1]
+        if self.D != self._model.dims():
+            raise ValueError("sample_initial returned the wrong dimension")
+        self._ws = Workspace(self.device)
+        self._stats = torch.empty(3, dtype=torch.float64, device=self.device)
+        self.last_indices = None
+        self.last_accept = None
+        self.weight_ess = []  # diagnostic only: the reference resamples unconditionally (smc.py:60)
+
+    # ---- reference surface -----------------------------------------------------------
+    def log_prior(self, theta):
+        return self._model.log_prior(theta)
+
+    def log_likelihood(self, theta):
+        return self._model.log_likelihood(theta)
+
+    def __iter__(self) -> Iterator[torch.Tensor]:
+        self.run()
+        return iter(self.thetas)
+
+    def run(self) -> None:
+        for n in range(1, self.N + 1):
+            self.transition(n)
+
+    def time(self, n: int) -> float:
+        return n / self.N
+
+    def transition(self, n: int, normals=None, acc_uniforms=None, res_uniforms=None) -> None:
+        """One temperature step (smc.py:46-60).  The optional arrays inject the
+        reference's recorded legacy-RNG streams (parity mode): proposal normals
+        [M, D], accept uniforms [M], resampling uniforms [M] (systematic: [1])."""
+        lib = L.lib()
+        Ml = self.thetas.shape[0]
+        st = stream_ptr(self.device)
+        logw = torch.empty(Ml, dtype=self.dtype, device=self.device)
+        acc = torch.empty(Ml, dtype=torch.int32, device=self.device)
+        if normals is not None:
+            normals = to_dev(normals, self.dtype, self.device).reshape(Ml, self.D)
+            acc_uniforms = to_dev(acc_uniforms, self.dtype, self.device).reshape(Ml)
+        rng = make_rng(self._seed, n, self._lo, normals, acc_uniforms, 1)
+        mode = L.RESAMPLE_MULTINOMIAL if self.resample == "multinomial" else L.RESAMPLE_SYSTEMATIC
+        with torch.cuda.device(self.device):
+            L.check(lib.bk_smc_move_weight(self._model.handle, self.thetas.data_ptr(), Ml, n, self.N,
+                                           self.kernel.scale, C.byref(rng), logw.data_ptr(),
+                                           acc.data_ptr(), st))
+            # --- the naturally global step: normaliser + resampling ---------------------
+            logw_all = D_.all_gather_cat(logw, self._group)      # [M]
+            thetas_all = D_.all_gather_cat(self.thetas, self._group)  # [M, D]
+            Mg = logw_all.shape[0]
+            wp, wn = self._ws.get(lib.bk_smc_resample_workspace_bytes(Mg))
+            L.check(lib.bk_smc_weight_stats(logw_all.data_ptr(), Mg, L.BK_F32 if self.dtype == torch.float32
+                                            else L.BK_F64, mode, self._stats.data_ptr(), wp, wn, st))
+            stats = self._stats.cpu()  # 3 doubles: shift, sum w, sum w^2
+            shift, total, total2 = float(stats[0]), float(stats[1]), float(stats[2])
+            self.weight_ess.append(total * total / total2 if total2 > 0 else float("nan"))
+            if res_uniforms is not None:
+                ru = to_dev(res_uniforms, self.dtype, self.device).reshape(-1)
+                if mode == L.RESAMPLE_MULTINOMIAL and ru.numel() == Mg and self._world > 1:
+                    ru = ru[self._lo:self._hi].contiguous()
+            else:
+                ru = None
+            idx = torch.empty(Ml, dtype=torch.int64, device=self.device)
+            rrng = make_rng(self._seed, n, 0)
+            L.check(lib.bk_smc_resample_indices(
+                logw_all.data_ptr(), Mg, L.BK_F32 if self.dtype == torch.float32 else L.BK_F64, mode,
+                shift, total if mode == L.RESAMPLE_MULTINOMIAL else 1.0, ptr(ru), C.byref(rrng), Ml,
+                self._lo, idx.data_ptr(), None, wp, wn, st))
+            new = torch.empty_like(self.thetas)
+            L.check(lib.bk_gather_rows(thetas_all.data_ptr(), idx.data_ptr(), Ml, self.D,
+                                       L.BK_F32 if self.dtype == torch.float32 else L.BK_F64,
+                                       new.data_ptr(), st))
+        self.thetas = new
+        self.last_indices = idx
+        self.last_accept = acc

@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Headline benchmark: HMC chain-steps/s on BASELINE config c2.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): HMCDiag, L=10
+leapfrog steps, 65,536 chains PER GPU on the 1000-dim dense-precision Gaussian
+(P = A A^T / D + I, A ~ N(0,1) from default_rng(0)); synthetic data, fp32
+device-Philox mode.  One "step" = one sample() of every chain (one chain-step
+per chain).  Chains shard across ranks with no communication (weak scaling).
+
+Prints ONE JSON line (rank 0).  `value` = chain-steps/s with the chain state
+resident in HBM; `e2e` = the same metric through the public Python API with
+HOST buffers (pinned host -> device copy of the chain state and device -> host
+copy of the draw + log density inside the timed region, every step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D = 1000
+L = 10
+EPS = 0.2            # accept ~0.85-0.9 on c2 (tuned with the oracle)
+CHAINS_PER_GPU = 65536
+METRIC = "hmc_chain_steps_per_s"
+UNIT = "chain-steps/s"
+
+
+def c2_precision():
+    import numpy as np
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(D, D))
+    return A @ A.T / D + np.eye(D)
+
+
+# --------------------------------------------------------------------------------
+# CPU baseline: the reference algorithm on host cores
+# --------------------------------------------------------------------------------
+def _cpu_chain_worker(args):
+    """One chain of HMCDiag on c2 for n draws; returns seconds.  Uses the
+    unmodified reference when baseline/_ref holds it, else the oracle port."""
+    n, seed, use_ref = args
+    import numpy as np
+    try:
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(limits=1)
+    except Exception:  # pragma: no cover
+        import contextlib
+        ctx = contextlib.nullcontext()
+    with ctx:
+        from oracle.models import DensePrecGauss
+        model = DensePrecGauss(c2_precision())
+        rng = np.random.default_rng(seed)
+        th0 = rng.normal(size=D)
+        if use_ref:
+            from oracle.record import load_reference
+            bkref = load_reference()
+            s = bkref.HMCDiag(model, EPS, L, init=th0, seed=seed)
+            s.sample()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                s.sample()
+            return time.perf_counter() - t0
+        from oracle import samplers as osm
+        zs, us = rng.standard_normal((n, D)), rng.random(n)
+        osm.hmc_diag(model, th0, zs[:1], us[:1], EPS, L)
+        t0 = time.perf_counter()
+        osm.hmc_diag(model, th0, zs, us, EPS, L)
+        return time.perf_counter() - t0
+
+
+def _ref_on_box() -> bool:
+    return os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "bayes_kit", "hmc.py"))
+
+
+def cpu_baseline_single(target_s=12.0):
+    """1 core, bounded sample: 1 chain x n draws of the c2 workload."""
+    use_ref = _ref_on_box()
+    t = _cpu_chain_worker((20, 0, use_ref))
+    n = max(20, int(target_s / max(t / 20, 1e-6)))
+    t = _cpu_chain_worker((n, 1, use_ref))
+    return {"value": n / t, "unit": UNIT, "cores": 1, "kind": "reference" if use_ref else "port",
+            "sample": f"1 chain x {n} draws of HMCDiag(L={L}, eps={EPS}) on the {D}-dim dense-precision "
+                      f"Gaussian, 1 BLAS thread; rate is per chain-step"}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU path on all host cores.  One step =
+    every worker process advances one chain by `draws` draws."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    use_ref = _ref_on_box()
+    t1 = _cpu_chain_worker((10, 0, use_ref)) / 10
+    draws = max(5, int(3.0 / t1))             # ~3 s of work per worker per step
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        for w in range(args.warmup):
+            pool.map(_cpu_chain_worker, [(max(2, draws // 10), 100 + c, use_ref) for c in range(cores)])
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            pool.map(_cpu_chain_worker, [(draws, 1000 * k + c, use_ref) for c in range(cores)])
+        dt = time.perf_counter() - t0
+    value = cores * draws * args.steps / dt
+    sample = (f"{cores} processes x 1 chain x {draws} draws per step of HMCDiag(L={L}, eps={EPS}) on the "
+              f"{D}-dim dense-precision Gaussian (1 BLAS thread per process)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"c2: HMCDiag L={L} eps={EPS}, {D}-dim dense-precision Gaussian, "
+                                   f"chains run independently on host cores"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores,
+                             "kind": "reference" if use_ref else "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# --------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.p, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.startswith("Active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import bayes_kit_b200 as bk
+    from bayes_kit_b200 import _lib
+    lib = _lib.lib()
+
+    C = args.chains
+    model = bk.DensePrecGauss(c2_precision(), dtype=torch.float32, device=dev)
+    # theta0 ~ N(0, I) per chain (the reference's default init, hmc.py:27); global chain ids
+    sampler = bk.HMCDiag(model, EPS, L, chains=C, seed=0, chain_offset=rank * C)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ------------------------------------------------
+    for _ in range(args.warmup):
+        sampler.sample_n(1)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    lib.bk_profile_enable(1)
+    launches0 = lib.bk_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    acc_sum = 0.0
+    ev0.record()
+    for _ in range(args.steps):
+        # every step writes a fresh 262 MB draw (> L2) and streams ~1.6 GB of state
+        sampler.sample_n(1)
+        acc_sum += 0.0
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.bk_launch_count() - launches0
+    lib.bk_profile_enable(0)
+    gms, gn = _lib.f64(0), _lib.u64(0)
+    lib.bk_profile_read(_lib.PROF_GRAD, gms, gn)
+    accept = float(sampler.last_accept.float().mean())
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t)
+    value = world * C * args.steps / (ms_max * 1e-3)
+
+    # ---- end to end through the public API with host buffers --------------------------
+    host_theta = torch.empty(C, D, dtype=torch.float32).pin_memory()
+    host_theta.copy_(sampler.theta)
+    host_draw = torch.empty(C, D, dtype=torch.float32).pin_memory()
+    host_lp = torch.empty(C, dtype=torch.float32).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        sampler._theta.copy_(host_theta, non_blocking=True)   # H2D: chain state
+        sampler._cache_valid.value = 0                        # state came from the host
+        th, lp = sampler.sample()
+        host_draw.copy_(th, non_blocking=True)                # D2H: the draw
+        host_lp.copy_(lp, non_blocking=True)                  # D2H: its log density
+        torch.cuda.current_stream().synchronize()
+        host_theta.copy_(host_draw)                           # host-side hand-off to the next step
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * C * e2e_steps / float(t)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the gradient GEMM) ----------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0   # fallback: B200_PROFILING.md sustained figure
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback"
+    flops_per_launch = 2.0 * C * D * D                       # 2*C*D^2 per gradient
+    g_avg_ms = gms.value / max(gn.value, 1)
+    achieved = flops_per_launch / (g_avg_ms * 1e-3) / 1e12 if gn.value else None
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
+                "kernel": "dense-precision gradient GEMM", "launches_timed": int(gn.value),
+                "avg_launch_ms": g_avg_ms, "share_of_step": gms.value / ms if ms else None,
+                "peak_source": peak_src}
+
+    cpu = None if args.no_cpu_baseline else cpu_baseline_single()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"c2: HMCDiag L={L} eps={EPS}, {C} chains/GPU x {D}-dim dense-precision "
+                               f"Gaussian (P=AA^T/D+I, seed 0), device Philox",
+                   "chains_per_gpu": C, "dims": D, "leapfrog_steps": L, "accept_rate": accept,
+                   "grad_evals_per_s": value * L,
+                   "l2": "inputs larger than L2 (>= 1.5 GB of chain state streamed per step)"},
+        "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": C * D * 4,
+                "d2h_bytes_per_step": C * D * 4 + C * 4, "steps": e2e_steps},
+        "gpu_launches": int(launches), "clocks": clk,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,233 @@
+/*
+ * bk.h -- C ABI of libbk_b200.so: the B200-native (sm_100a) replacement for the
+ * data-parallel sampling hot path of flatironinstitute/bayes-kit.
+ *
+ * The reference has NO FFI layer: its boundary is a pair of Python structural
+ * protocols (bayes_kit/typing.py:15-42) called once per gradient from the
+ * interpreter.  This header is what a reference-side binding (ctypes, see
+ * INTEGRATION.md) binds instead.  Every entry point names the reference
+ * function(s) it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain C types only; no torch / CUDA types in signatures
+ *     (`stream` is a cudaStream_t passed as void*; 0 = default stream).
+ *   - every function returns int: 0 = BK_OK, <0 = BK_E_*; bk_last_error()
+ *     gives the thread-local message.
+ *   - the CALLER owns every buffer.  All pointers are DEVICE pointers unless
+ *     a name ends in _host.  The library never frees caller memory and
+ *     allocates no device memory: scratch is passed in (`ws`, sized by the
+ *     matching *_workspace_bytes()).
+ *   - all work is enqueued asynchronously on `stream`; no hidden syncs.
+ *   - tensors are dense row-major: theta [C, D], draws [n, C, D].
+ *   - `dtype`: BK_F32 (timed mode) or BK_F64 (parity mode: separate
+ *     multiply/add roundings in NumPy's association order).
+ */
+#ifndef BK_B200_H
+#define BK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BK_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define BK_API __attribute__((visibility("default")))
+#else
+#define BK_API
+#endif
+
+enum { BK_OK = 0, BK_E_INVALID = -1, BK_E_UNSUPPORTED = -2, BK_E_CUDA = -3,
+       BK_E_WORKSPACE = -4, BK_E_HANDLE = -5 };
+
+enum { BK_F32 = 0, BK_F64 = 1 };
+
+/* model plugin kinds (device-side log density + gradient; replaces the Python
+ * callbacks model.log_density / log_density_gradient / log_prior /
+ * log_likelihood, typing.py:15-42) */
+enum { BK_MODEL_ISO_GAUSS = 0,        /* -0.5 |theta|^2 / sigma^2                          */
+       BK_MODEL_DIAG_GAUSS = 1,       /* -0.5 sum prec_i (theta_i - mu_i)^2                */
+       BK_MODEL_DENSE_PREC_GAUSS = 2, /* -0.5 (theta-mu)^T P (theta-mu)                    */
+       BK_MODEL_HIER_LOGREG = 3,      /* hierarchical logistic regression      */
+       BK_MODEL_GAUSS_PRIOR_LIK = 4   /* prior N(m0, 1/p0) x likelihood N(mu, 1/pl) (SMC)  */ };
+
+enum { BK_RNG_PHILOX = 0,   /* device Philox4x32-10, counter = (block, tag, chain, draw) */
+       BK_RNG_INJECTED = 1  /* pre-drawn streams in the reference's consumption order */ };
+
+enum { BK_RESAMPLE_MULTINOMIAL = 0, /* smc.py:64-75 (legacy np.random.choice)           */
+       BK_RESAMPLE_SYSTEMATIC = 1   /* north_star item 2; log-sum-exp normalised        */ };
+
+enum { BK_IAT_IPSE = 0, BK_IAT_IMSE = 1 };
+
+typedef struct bk_model_desc {
+    int32_t kind;        /* BK_MODEL_*                                                  */
+    int32_t dtype;       /* dtype of every array below                                  */
+    int64_t dims;        /* D (HIER_LOGREG: Dx + 2)                                     */
+    double  sigma;       /* ISO_GAUSS                                                   */
+    const void* mu;      /* [D] DIAG/DENSE mean (NULL = 0); GAUSS_PRIOR_LIK lik. mean    */
+    const void* prec;    /* [D] DIAG precisions;            GAUSS_PRIOR_LIK lik. prec    */
+    const void* P;       /* [D, D] DENSE precision, row-major, symmetric                 */
+    const void* m0;      /* [D] GAUSS_PRIOR_LIK prior mean                               */
+    const void* p0;      /* [D] GAUSS_PRIOR_LIK prior precisions                         */
+    const void* X;       /* [N, Dx] HIER_LOGREG design matrix                            */
+    const void* y;       /* [N] HIER_LOGREG 0/1 responses                                */
+    int64_t n_obs;       /* N                                                            */
+} bk_model_desc;
+
+typedef struct bk_rng {
+    int32_t  mode;          /* BK_RNG_*                                                  */
+    int32_t  n_uniform;     /* INJECTED: uniforms per (draw, chain) (1; 2K for DrGHMC)   */
+    uint64_t seed;          /* PHILOX key                                                */
+    uint64_t draw_offset;   /* PHILOX: index of this call's first draw                   */
+    uint64_t chain_offset;  /* PHILOX: global id of local chain 0 (multi-GPU shards)     */
+    const void* normals;    /* INJECTED: [n_draws, C, D] standard normals (dtype)        */
+    const void* uniforms;   /* INJECTED: [n_draws, C, n_uniform] uniforms in [0,1)       */
+} bk_rng;
+
+/* per-call outputs shared by the MCMC samplers; any pointer may be NULL */
+typedef struct bk_draw_out {
+    void*    draws;   /* [n_draws, C, D]                                                 */
+    void*    logp;    /* [n_draws, C] value sample() returns (HMC/DrGHMC: JOINT logp)    */
+    int32_t* accept;  /* [n_draws, C] 1 = proposal accepted                              */
+} bk_draw_out;
+
+BK_API const char* bk_last_error(void);
+BK_API int bk_abi_version(void);
+/* number of kernels launched by this process through the library so far */
+BK_API uint64_t bk_launch_count(void);
+
+/* Optional in-library CUDA-event timing of the dominant kernels, recorded on
+ * the launch stream (bench.py's live roofline measurement).  bk_profile_read
+ * synchronises the recorded events, returns the summed device time and launch
+ * count of `tag` since the last read, and resets that tag. */
+enum { BK_PROF_GRAD = 0,      /* model gradient kernel (GEMM for the dense plugin) */
+       BK_PROF_SAMPLER = 1,   /* fused sampler kernel                              */
+       BK_PROF_NTAGS = 4 };
+BK_API int bk_profile_enable(int32_t on);
+BK_API int bk_profile_read(int32_t tag, double* total_ms_out, uint64_t* launches_out);
+
+/* ---- model plugins (typing.py:15-42) ------------------------------------ */
+BK_API size_t bk_model_workspace_bytes(const bk_model_desc* desc);
+/* `ws` (device, bk_model_workspace_bytes) holds derived operands (bf16 splits
+ * of P, P*mu, ...) and must outlive the handle. */
+BK_API int bk_model_create(const bk_model_desc* desc, void* ws, size_t ws_bytes, void* stream,
+                    uint64_t* handle_out);
+BK_API int bk_model_destroy(uint64_t handle);
+BK_API int64_t bk_model_dims(uint64_t handle);
+BK_API size_t bk_model_eval_workspace_bytes(uint64_t handle, int64_t C);
+/* model.log_density / log_density_gradient, batched: theta [C,D] -> lp [C],
+ * grad [C,D] (grad may be NULL).  hmc.py:38,45,50; mala.py:31,46 */
+BK_API int bk_model_log_density_gradient(uint64_t handle, const void* theta, int64_t C, void* lp_out,
+                                  void* grad_out, void* ws, size_t ws_bytes, void* stream);
+/* log_prior / log_likelihood (smc.py:29-33), GAUSS_PRIOR_LIK only */
+BK_API int bk_model_log_prior_likelihood(uint64_t handle, const void* theta, int64_t C,
+                                  void* log_prior_out, void* log_lik_out, void* stream);
+
+/* ---- HMCDiag (hmc.py:9-63): n_draws calls of sample() for C chains ------- */
+BK_API size_t bk_hmc_diag_workspace_bytes(uint64_t handle, int64_t C);
+/* theta [C,D] in/out.  lp_cache [C] / grad_cache [C,D] hold log p and its
+ * gradient at theta (in/out, only read when *cache_valid != 0; refreshed and
+ * *cache_valid set to 1 on return; used by the GEMM-gradient models, ignored by
+ * the fused separable kernels -- pass NULL there if you like).
+ * metric: [D] or NULL (identity; the reference only supports None/size-1). */
+BK_API int bk_hmc_diag_sample(uint64_t handle, void* theta, void* lp_cache, void* grad_cache,
+                       int32_t* cache_valid_host, int64_t C, double stepsize, int32_t steps,
+                       const void* metric, int64_t n_draws, const bk_rng* rng,
+                       const bk_draw_out* out, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- MALA (mala.py:15-79) ----------------------------------------------- */
+BK_API size_t bk_mala_workspace_bytes(uint64_t handle, int64_t C);
+BK_API int bk_mala_sample(uint64_t handle, void* theta, void* lp_cache, void* grad_cache,
+                   int32_t* cache_valid_host, int64_t C, double epsilon, int64_t n_draws,
+                   const bk_rng* rng, const bk_draw_out* out, void* ws, size_t ws_bytes,
+                   void* stream);
+
+/* ---- Metropolis / MetropolisHastings with the built-in Gaussian random-walk
+ * proposal theta' = theta + scale*z (metropolis.py:79-155; proposal family of
+ * smc.py:79-89 / test_metropolis.py:114).  hastings != 0 also evaluates the
+ * (cancelling) symmetric transition terms like MetropolisHastings does. ---- */
+BK_API size_t bk_mh_rw_workspace_bytes(uint64_t handle, int64_t C);
+BK_API int bk_mh_rw_sample(uint64_t handle, void* theta, void* lp_cache, int32_t* cache_valid_host,
+                    int64_t C, double scale, int32_t hastings, int64_t n_draws,
+                    const bk_rng* rng, const bk_draw_out* out, void* ws, size_t ws_bytes,
+                    void* stream);
+
+/* ---- DrGhmcDiag (drghmc.py:37-446) --------------------------------------
+ * theta, rho [C,D] in/out; step_sizes_host[K], step_counts_host[K].
+ * uniforms are consumed retry-test then accept-test per attempt
+ * (drghmc.py:370,378): rng->n_uniform must be 2K in INJECTED mode. */
+BK_API size_t bk_drghmc_workspace_bytes(uint64_t handle, int64_t C, int32_t max_proposals);
+BK_API int bk_drghmc_sample(uint64_t handle, void* theta, void* rho, int64_t C, int32_t max_proposals,
+                     const double* step_sizes_host, const int32_t* step_counts_host,
+                     double damping, int32_t prob_retry, const void* metric, int64_t n_draws,
+                     const bk_rng* rng, const bk_draw_out* out, int32_t* n_uniform_used_out,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* ---- TemperedLikelihoodSMC (smc.py:12-89) -------------------------------- */
+/* One temperature step n (1-based) of T for M particles, RW-Metropolis kernel
+ * of smc.py:79-89 targeting time(n-1) (smc.py:54-57) fused with the importance
+ * log-weights lp_n - lp_{n-1} of smc.py:67-70.  thetas [M,D] in/out;
+ * logw_out [M].  rng: normals [1,M,D], uniforms [1,M,1] when INJECTED;
+ * draw_offset = n. */
+BK_API int bk_smc_move_weight(uint64_t handle, void* thetas, int64_t M, int32_t n, int32_t T,
+                       double scale, const bk_rng* rng, void* logw_out, int32_t* accept_out,
+                       void* stream);
+BK_API size_t bk_smc_resample_workspace_bytes(int64_t M);
+/* local reduction of the log-weights: stats_out[0] = max, [1] = sum exp(logw -
+ * shift), [2] = sum exp(..)^2 where shift = max (SYSTEMATIC) or 0
+ * (MULTINOMIAL, the reference does not shift: smc.py:67); always fp64.  The
+ * multi-GPU path all-reduces these between this call and bk_smc_resample. */
+BK_API int bk_smc_weight_stats(const void* logw, int64_t M, int32_t dtype, int32_t mode,
+                        double* stats_out, void* ws, size_t ws_bytes, void* stream);
+/* indices of importance_resample (smc.py:64-75) for M weights (multi-GPU:
+ * the all-gathered log-weights, so every rank builds the same CDF):
+ *   p_i = exp(logw_i - shift) / total;  cdf = cumsum(p);  cdf /= cdf[-1]
+ * MULTINOMIAL: idx_i = searchsorted(cdf, u_i, 'right') (== legacy
+ * np.random.choice) with u [n_points] INJECTED via
+ * `uniforms`, else Philox keyed by the global point index.  SYSTEMATIC:
+ * points (point_offset + i + u0) / M with u0 = uniforms[0] or Philox; pass
+ * total = 1 (the CDF is normalised by its last entry).  This call resolves
+ * the n_points points starting at global point index point_offset (a rank's
+ * slice).  idx_out [n_points] int64; cdf_out [M] f64 or NULL (scratch in ws). */
+BK_API int bk_smc_resample_indices(const void* logw, int64_t M, int32_t dtype, int32_t mode,
+                            double shift, double total, const void* uniforms, const bk_rng* rng,
+                            int64_t n_points, int64_t point_offset, int64_t* idx_out,
+                            void* cdf_out, void* ws, size_t ws_bytes, void* stream);
+/* thetas[idxs] (smc.py:75): out [M,D] = src[idx] */
+BK_API int bk_gather_rows(const void* src, const int64_t* idx, int64_t M, int64_t D, int32_t dtype,
+                   void* out, void* stream);
+
+/* ---- diagnostics -------------------------------------------------------- */
+/* Where the draws of series s live: element t of series s is
+ *   x[(s / n_inner) * outer_stride + (s % n_inner) * inner_stride + t * draw_stride]
+ * (strides in elements), so [chains, draws], [chains, draws, params] and the
+ * samplers' own [draws, chains, params] output are all consumed in place. */
+typedef struct bk_series_layout {
+    int64_t n_series, n_draws, n_inner, outer_stride, inner_stride, draw_stride;
+} bk_series_layout;
+
+BK_API size_t bk_autocorr_workspace_bytes(int64_t n_series, int64_t N);
+/* autocorr.py:6-33 -- all N lags of the biased estimator, fp64 accumulate;
+ * out [n_series, N] f64 */
+BK_API int bk_autocorr(const void* x, int32_t dtype, const bk_series_layout* layout, double* out,
+                       void* ws, size_t ws_bytes, void* stream);
+/* iat_ipse/iat_imse (iat.py:46-135) and ess_* (ess.py:5-69); outputs [n_series] f64 */
+BK_API int bk_iat_ess(const void* x, int32_t dtype, const bk_series_layout* layout, int32_t estimator,
+                      double* iat_out, double* ess_out, void* ws, size_t ws_bytes, void* stream);
+/* per-series mean and ddof=1 variance (rhat.py:165-166); outputs [n_series] f64 */
+BK_API int bk_chain_moments(const void* x, int32_t dtype, const bk_series_layout* layout,
+                            double* mean_out, double* var_out, void* stream);
+/* rhat (rhat.py:111-171) from per-chain moments laid out [n_chains, n_params];
+ * lengths [n_chains] (ragged allowed) or NULL with common length N.
+ * out [n_params] f64 */
+BK_API int bk_rhat_from_moments(const double* mean, const double* var, const int64_t* lengths,
+                                int64_t N, int64_t n_chains, int64_t n_params, double* out,
+                                void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BK_B200_H */

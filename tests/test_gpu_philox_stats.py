@@ -1,0 +1,145 @@
+"""fp32 / device-Philox mode: statistical recovery (posterior moments within
+4 MCSE, BASELINE north_star), reproducibility, seed sensitivity, and the
+reference's cross-algorithm equivalences -- mirroring test_hmc.py:38-65,
+test_mala.py:9-60, test_metropolis.py:106-254, test_equivalencies.py:12-32,
+test_drghmc.py:97-148, test_tempered_smc.py:8-30."""
+import numpy as np
+import pytest
+import torch
+
+from _dev import np_
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_moments(draws, mean, var, ess_per_param):
+    """|mean_hat - mean| <= 4 MCSE and |var_hat - var| <= 4 MCSE (Gaussian target)."""
+    d = np_(draws).reshape(-1, draws.shape[-1]).astype(np.float64)
+    mcse_mean = np.sqrt(var / ess_per_param)
+    mcse_var = var * np.sqrt(2.0 / ess_per_param)
+    assert np.all(np.abs(d.mean(0) - mean) <= 4 * mcse_mean + 1e-3), np.abs(d.mean(0) - mean).max()
+    assert np.all(np.abs(d.var(0, ddof=1) - var) <= 4 * mcse_var + 1e-3)
+
+
+def _ess_total(bk, draws):
+    # draws [n, C, D] (sampler layout): sum over chains of per-chain ESS, per parameter
+    return np_(bk.ess(draws, draws_first=True)).sum(0)
+
+
+def test_hmc_std_normal(bk):  # test_hmc.py:38-51
+    model = bk.IsoGauss(100)
+    s = bk.HMCDiag(model, 0.25, 10, chains=512, seed=1)
+    s.sample_n(50, keep_draws=False)
+    draws, _ = s.sample_n(400)
+    _check_moments(draws, np.zeros(100), np.ones(100), _ess_total(bk, draws))
+    assert 0.8 < float(s.last_accept.float().mean()) <= 1.0
+
+
+def test_mala_std_normal(bk):  # test_mala.py:9-23
+    model = bk.IsoGauss(10)
+    s = bk.MALA(model, 0.3, chains=512, seed=2)
+    s.sample_n(100, keep_draws=False)
+    draws, _ = s.sample_n(1000)
+    _check_moments(draws, np.zeros(10), np.ones(10), _ess_total(bk, draws))
+
+
+def test_metropolis_diag(bk):  # test_metropolis.py:106-123
+    mu, prec = np.array([1.0, -2.0, 0.5]), np.array([1.0, 4.0, 0.25])
+    model = bk.DiagGauss(mu, prec)
+    s = bk.Metropolis(model, bk.GaussianRW(1.0), chains=1024, seed=3)
+    s.sample_n(300, keep_draws=False)
+    draws, _ = s.sample_n(2000)
+    _check_moments(draws, mu, 1 / prec, _ess_total(bk, draws))
+
+
+def test_drghmc_std_normal(bk):  # test_drghmc.py:97-117
+    model = bk.IsoGauss(5)
+    s = bk.DrGhmcDiag(model, 2, [1.9, 0.5 / 5], [10, 20], 0.9, chains=512, seed=4)
+    s.sample_n(100, keep_draws=False)
+    draws, _ = s.sample_n(1000)
+    _check_moments(draws, np.zeros(5), np.ones(5), _ess_total(bk, draws))
+
+
+def test_dense_hmc_moments(bk):
+    from oracle.models import DensePrecGauss
+    D = 32
+    P = DensePrecGauss.c2_precision(D, 5)
+    cov = np.linalg.inv(P)
+    s = bk.HMCDiag(bk.DensePrecGauss(P), 0.15, 8, chains=1024, seed=5)
+    s.sample_n(60, keep_draws=False)
+    draws, _ = s.sample_n(300)
+    _check_moments(draws, np.zeros(D), np.diag(cov), _ess_total(bk, draws))
+
+
+def test_reproducible_and_seed_sensitive(bk):  # test_hmc.py:54-65, test_mala.py:44-60
+    model = bk.IsoGauss(7)
+    init = np.random.default_rng(0).normal(size=(6, 7))
+    for mk in (lambda sd: bk.HMCDiag(model, 0.25, 10, init=init, seed=sd),
+               lambda sd: bk.MALA(model, 0.3, init=init, seed=sd),
+               lambda sd: bk.Metropolis(model, bk.GaussianRW(0.5), init=init, seed=sd),
+               lambda sd: bk.DrGhmcDiag(model, 2, [0.9, 0.3], [3, 6], 0.5, init=init, seed=sd)):
+        a, b, c = mk(123), mk(123), mk(321)
+        da = torch.stack([a.sample()[0] for _ in range(25)])
+        db = torch.stack([next(b)[0] for _ in range(25)])     # next() == sample()
+        dc = torch.stack([c.sample()[0] for _ in range(25)])
+        assert torch.equal(da, db)
+        assert not torch.equal(da, dc)
+        # one call of 25 draws == 25 calls of one draw (Philox counter = draw index)
+        dd, _ = mk(123).sample_n(25)
+        assert torch.equal(da, dd)
+
+
+def test_hmc_one_step_is_mala(bk):  # test_equivalencies.py:12-32
+    model = bk.IsoGauss(1, dtype=torch.float64)
+    init = np.array([0.2])
+    eps = 0.02
+    hmc = bk.HMCDiag(model, eps, 1, init=init, seed=123)
+    mala = bk.MALA(model, 0.5 * eps ** 2, init=init, seed=123)
+    d1 = np_(hmc.sample_n(50)[0]); d2 = np_(mala.sample_n(50)[0])
+    np.testing.assert_array_almost_equal(d1, d2)
+    assert len(np.unique(d1)) > 20
+
+
+def test_metropolis_equals_mh_symmetric(bk):  # test_equivalencies.py:35-60
+    model = bk.IsoGauss(3)
+    init = np.zeros((4, 3))
+    prop = bk.GaussianRW(0.7)
+    a = bk.Metropolis(model, prop, init=init, seed=1848)
+    b = bk.MetropolisHastings(model, prop, prop.transition_lp, init=init, seed=1848)
+    assert torch.equal(a.sample_n(25)[0], b.sample_n(25)[0])
+
+
+def test_single_chain_surface(bk):  # test_theta_initialization.py:34-54
+    model = bk.IsoGauss(3)
+    init = np.array([3.0, 3.0, 3.0])
+    for s in (bk.HMCDiag(model, 0.25, 10, init=init), bk.MALA(model, 0.5, init=init),
+              bk.Metropolis(model, bk.GaussianRW(1.0), init=init)):
+        np.testing.assert_array_equal(np_(s.theta), init)
+        th, lp = s.sample()
+        assert th.shape == (3,) and lp.dim() == 0
+    s = bk.HMCDiag(model, 0.25, 10, init=np.array([]))   # empty init == no init
+    assert s.theta.shape == (3,)
+
+
+def test_shard_invariance(bk):
+    """Chains [lo, hi) of a sharded run == the same chains of the full run
+    (Philox keyed by the global chain id)."""
+    model = bk.IsoGauss(20)
+    init = np.random.default_rng(1).normal(size=(64, 20))
+    full = bk.HMCDiag(model, 0.2, 5, init=init, seed=9).sample_n(10)[0]
+    part = bk.HMCDiag(model, 0.2, 5, init=init[40:64], seed=9, chain_offset=40).sample_n(10)[0]
+    assert torch.equal(full[:, 40:64], part)
+
+
+def test_smc_posterior(bk):  # test_tempered_smc.py:8-30 (Gaussian analogue)
+    D, M, T = 2, 20000, 40
+    mu = np.array([1.0, -0.5])
+    model = bk.GaussPriorLik(np.zeros(D), np.ones(D), mu, 4 * np.ones(D))
+    th0 = np.random.default_rng(0).normal(size=(M, D))
+    for mode in ("multinomial", "systematic"):
+        smc = bk.TemperedLikelihoodSMC(model, M, T, th0, bk.metropolis_kernel(0.5), resample=mode, seed=11)
+        smc.run()
+        th = np_(smc.thetas).astype(np.float64)
+        np.testing.assert_allclose(th.mean(0), 0.8 * mu, atol=0.05)
+        np.testing.assert_allclose(th.var(0, ddof=1), 0.2 * np.ones(D), atol=0.05)
+        assert len(smc.weight_ess) == T and all(1 <= e <= M + 1e-6 for e in smc.weight_ess)
