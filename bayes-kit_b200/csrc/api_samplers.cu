@@ -3,6 +3,7 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include "dense_tc.h"
 #include "sampler_generic.h"
 
 using namespace bk;
@@ -92,6 +93,12 @@ int hmc_t(const Model& m, void* theta, void* lp, void* grad, int32_t* valid, int
         return launch_sep_sampler<T>(a, st);
     }
     BK_CHECK_ARG(lp && grad, "bk_hmc_diag_sample: lp_cache/grad_cache are required for this model");
+    if constexpr (sizeof(T) == 4) {
+        // tensor-core pipeline: L-1 fused bf16 steps + one split-precision endpoint gradient
+        if (dense_tc_enabled(m) && L >= 1)
+            return dense_tc_hmc(m, (float*)theta, (float*)lp, (float*)grad, valid, C, eps, L,
+                                (const float*)metric, n, rng, out, ws, wsb, st);
+    }
     GenArgs<T> p;
     fill_gen(p, m, theta, lp, grad, C, metric, n, rng, out);
     p.eps = (T)eps;
@@ -148,6 +155,10 @@ size_t sampler_ws(uint64_t h, int64_t C) {
     const Model* m = get_model(h);
     if (!m || C <= 0) return 0;
     if (m->separable() && m->d.dims <= SEP_MAX_D && !force_generic()) return 0;
+    if (dense_tc_enabled(*m)) {
+        size_t a = dense_tc_hmc_ws_bytes(*m, C), b = generic_ws_bytes<float>(*m, C);
+        return a > b ? a : b;
+    }
     return m->d.dtype == BK_F64 ? generic_ws_bytes<double>(*m, C) : generic_ws_bytes<float>(*m, C);
 }
 

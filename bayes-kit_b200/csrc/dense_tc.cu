@@ -1,0 +1,738 @@
+// Dense-precision Gaussian on the 5th-gen tensor cores (fp32 timed mode).
+//
+// One leapfrog step of C chains is   G^T[d, c] = sum_k P[d, k] * Theta[c, k]
+// (M = dims, N = chains, K = dims): a TMA-fed tcgen05 GEMM with fp32
+// accumulators in TMEM.  A = bf16(P) tile [128 dims x 64 k], B = bf16(theta)
+// tile [256 chains x 64 k], both K-major with the 128-byte swizzle, staged by a
+// 4-deep TMA/mbarrier ring.  TMEM lanes are DIMS and TMEM columns are CHAINS,
+// so in the epilogue a warp's 32 lanes touch 32 consecutive dims of one chain:
+// every global access of the fused leapfrog update
+//        r += eps * m * g ;  q += eps * r ;  q_bf16(next operand) = bf16(q)
+// is a coalesced 128-byte row segment, straight from registers (no smem
+// staging).  The accumulator is double-buffered (2 x 256 TMEM columns) so the
+// epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Precision: interior leapfrog gradients use bf16 operands (the leapfrog map
+// stays a volume-preserving, reversible shear for ANY deterministic gradient
+// function); the endpoint gradient that enters the Hamiltonian is computed
+// with a 3-pass bf16 split (P_hi*q_hi + P_hi*q_lo + P_lo*q_hi, ~2^-16
+// relative) so the Metropolis test sees fp32-accurate energies.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator +
+// single-thread MMA issuer, warps 2..5 = epilogue (TMEM lane quarter = warp%4).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "dense_tc.h"
+#include "sep_common.cuh"
+
+namespace bk {
+
+namespace tc {
+
+constexpr int BM = 128;      // dims per tile  (UMMA M, TMEM lanes)
+constexpr int BN = 256;      // chains per tile (UMMA N, TMEM columns)
+constexpr int BK = 64;       // k per stage (128 bytes of bf16 = one swizzle atom row)
+constexpr int UK = 16;       // UMMA K for bf16
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_BYTES = BN * BK * 2;   // 32 KB
+constexpr int SMEM_TILES = STAGES * (A_BYTES + B_BYTES);
+constexpr int SMEM_BYTES = SMEM_TILES + 256 + 1024;  // + barriers + 1024B alignment slack
+constexpr int EPI_WARPS = 8;            // 2 per TMEM lane quarter (column halves)
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
+constexpr uint32_t TMEM_COLS = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024u >> 4) << 32;           // stride byte offset = 1024 B, bits [32,46)
+    d |= (uint64_t)1 << 46;                      // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                      // layout type: SWIZZLE_128B
+    return d;
+}
+// kind::f16, A = B = bf16, D = f32, both K-major, M = 128, N = 256
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                           ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+          "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+          "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+          "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+          "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct StepArgs {
+    int mode;          // TC_MODE_STEP | TC_MODE_GRAD
+    int n_pass;        // 1 (bf16) or 3 (bf16x3 split)
+    int64_t C;
+    int D, Dp;
+    int m_tiles;
+    int64_t n_tiles;
+    int kblocks;       // Dp / BK
+    float eps;
+    const float* metric;  // [D] or NULL
+    const float* cvec;    // [D] P*mu or NULL
+    float* r;             // [C, D]  (STEP: in/out)
+    float* q;             // [C, D]  (STEP: in/out)
+    __nv_bfloat16* q_hi_next;  // [C, Dp] (STEP)
+    __nv_bfloat16* q_lo_next;  // [C, Dp] or NULL
+    float* g_out;         // [C, D]  (GRAD)
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+           const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
+           const StepArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for the 128B swizzle atoms
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = base, sB = base + STAGES * A_BYTES;
+    const uint32_t bars = base + SMEM_TILES;
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto empty = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto tfull = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+    auto tempty = [&](int s) { return bars + 8u * (2 * STAGES + 2 + s); };
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 32 * EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int64_t total_tiles = a.n_tiles * a.m_tiles;
+    const int iters = a.n_pass * a.kblocks;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_tile = (int)(tile % a.m_tiles);
+                const int64_t n_tile = tile / a.m_tiles;
+                for (int it = 0; it < iters; ++it) {
+                    const int pass = it / a.kblocks, kb = it % a.kblocks;
+                    // pass 0: (A_hi, B_hi)  pass 1: (A_hi, B_lo)  pass 2: (A_lo, B_hi)
+                    const CUtensorMap* ma = pass == 2 ? &mapA1 : &mapA0;
+                    const CUtensorMap* mb = pass == 1 ? &mapB1 : &mapB0;
+                    mbar_wait(empty(stage), phase ^ 1u);
+                    mbar_expect_tx(full(stage), A_BYTES + B_BYTES);
+                    tma_load_2d(sA + stage * A_BYTES, ma, full(stage), kb * BK, m_tile * BM);
+                    tma_load_2d(sB + stage * B_BYTES, mb, full(stage), kb * BK, (int)(n_tile * BN));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(tempty(acc), acc_phase ^ 1u);   // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+                for (int it = 0; it < iters; ++it) {
+                    mbar_wait(full(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a0 = sA + stage * A_BYTES, b0 = sB + stage * B_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k)
+                        umma(d_tmem, umma_desc(a0 + k * UK * 2), umma_desc(b0 + k * UK * 2),
+                             (it | k) != 0 ? 1u : 0u);
+                    umma_commit(empty(stage));            // smem slot reusable once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(tfull(acc));                  // accumulator ready for the epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ================= epilogue: 8 warps, lane = dim, registers = chains =================
+        // warp -> TMEM lane quarter (warp % 4) and column half; each warp walks its 4
+        // chunks of 32 chains with the NEXT chunk's r/q loads already in flight
+        // (issued before the accumulator is even ready), so ~64 KB per SM stay
+        // outstanding and the HBM latency is covered.
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int NCH = BN / 32 / 2;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_tile = (int)(tile % a.m_tiles);
+            const int64_t n_tile = tile / a.m_tiles;
+            const int d = m_tile * BM + quarter * 32 + lane;
+            const bool d_ok = d < a.D;
+            const float cv = (a.cvec && d_ok) ? a.cvec[d] : 0.0f;
+            const float em = a.eps * ((a.metric && d_ok) ? a.metric[d] : 1.0f);
+            const uint32_t t0 = tmem_base + (uint32_t)acc * BN + ((uint32_t)(quarter * 32) << 16) +
+                                (uint32_t)(half * NCH * 32);
+            const int64_t cbase = n_tile * BN + half * NCH * 32;
+            if (a.mode == TC_MODE_GRAD) {
+                mbar_wait(tfull(acc), acc_phase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int ch = 0; ch < NCH; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(t0 + ch * 32, v);
+                    const int64_t c0 = cbase + ch * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int64_t c = c0 + j;
+                        if (d_ok && c < a.C) a.g_out[c * a.D + d] = cv - __uint_as_float(v[j]);
+                    }
+                }
+            } else {
+                // chunks of CW chains; two chunks of r/q loads stay in flight ahead of the math
+                constexpr int CW = 16, NC = NCH * 32 / CW;
+                const bool full_tile = d_ok && cbase + NCH * 32 <= a.C;   // no per-element bounds
+                const int64_t e0 = cbase * a.D + d;
+                const float* rp = a.r + e0;
+                const float* qp = a.q + e0;
+                float* rw = a.r + e0;
+                float* qw = a.q + e0;
+                __nv_bfloat16* hw = a.q_hi_next + cbase * a.Dp + d;
+                __nv_bfloat16* lw = a.q_lo_next ? a.q_lo_next + cbase * a.Dp + d : nullptr;
+                const int D = a.D, Dp = a.Dp;
+                const float eps = a.eps;
+                auto load = [&](int ch, float (&rb)[CW], float (&qb)[CW]) {
+                    const int64_t o = (int64_t)ch * CW * D;
+                    if (full_tile) {
+#pragma unroll
+                        for (int j = 0; j < CW; ++j) {
+                            rb[j] = __ldcs(rp + o + (int64_t)j * D);
+                            qb[j] = __ldcs(qp + o + (int64_t)j * D);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CW; ++j) {
+                            const bool ok = d_ok && cbase + ch * CW + j < a.C;
+                            rb[j] = ok ? rp[o + (int64_t)j * D] : 0.0f;
+                            qb[j] = ok ? qp[o + (int64_t)j * D] : 0.0f;
+                        }
+                    }
+                };
+                auto process = [&](int ch, const float (&rb)[CW], const float (&qb)[CW]) {
+                    uint32_t v[CW];
+                    tmem_ld16(t0 + ch * CW, v);
+                    const int64_t o = (int64_t)ch * CW * D, ob = (int64_t)ch * CW * Dp;
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) {
+                        if (full_tile || (d_ok && cbase + ch * CW + j < a.C)) {
+                            const float g = cv - __uint_as_float(v[j]);
+                            const float rn = fmaf(em, g, rb[j]);    // r += eps * m * g
+                            const float qn = fmaf(eps, rn, qb[j]);  // q += eps * r
+                            __stcs(rw + o + (int64_t)j * D, rn);
+                            __stcs(qw + o + (int64_t)j * D, qn);
+                            const __nv_bfloat16 hi = __float2bfloat16_rn(qn);
+                            hw[ob + (int64_t)j * Dp] = hi;
+                            if (lw) lw[ob + (int64_t)j * Dp] = __float2bfloat16_rn(qn - __bfloat162float(hi));
+                        }
+                    }
+                };
+                float r0[CW], q0[CW], r1[CW], q1[CW], r2[CW], q2[CW];
+                load(0, r0, q0);
+                load(1, r1, q1);
+                mbar_wait(tfull(acc), acc_phase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int ch = 0; ch < NC; ch += 3) {
+                    if (ch + 2 < NC) load(ch + 2, r2, q2);
+                    process(ch, r0, q0);
+                    if (ch + 1 < NC) {
+                        if (ch + 3 < NC) load(ch + 3, r0, q0);
+                        process(ch + 1, r1, q1);
+                    }
+                    if (ch + 2 < NC) {
+                        if (ch + 4 < NC) load(ch + 4, r1, q1);
+                        process(ch + 2, r2, q2);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// ---- operand preparation ---------------------------------------------------------
+// P [D,D] fp32 -> zero-padded bf16 hi/lo [Dp,Dp]
+__global__ void k_split_matrix(const float* __restrict__ P, int D, int Dp, __nv_bfloat16* __restrict__ hi,
+                               __nv_bfloat16* __restrict__ lo) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)Dp * Dp) return;
+    int r = (int)(i / Dp), c = (int)(i % Dp);
+    float v = (r < D && c < D) ? P[(int64_t)r * D + c] : 0.0f;
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// cvec = P * mu (fp64 accumulate), one warp per row
+__global__ void k_pmu(const float* __restrict__ P, const float* __restrict__ mu, int D, float* __restrict__ out) {
+    int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (r >= D) return;
+    double s = 0;
+    for (int k = lane; k < D; k += 32) s += (double)P[(int64_t)r * D + k] * (double)mu[k];
+    s = warp_sum(s);
+    if (lane == 0) out[r] = (float)s;
+}
+
+// theta [C,D] fp32 -> bf16 hi (/lo) [C,Dp]; pad columns untouched (zeroed once)
+__global__ void k_split_rows(const float* __restrict__ x, int64_t C, int D, int Dp,
+                             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C * D) return;
+    int64_t c = i / D;
+    int d = (int)(i % D);
+    float v = x[i];
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[c * Dp + d] = h;
+    if (lo) lo[c * Dp + d] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// ---- HMC begin / end around the tensor-core steps (fp32) ----------------------------
+struct HmcTcArgs {
+    float *theta, *lp, *grad;   // state
+    float *q, *r, *gq, *h0;     // workspace
+    __nv_bfloat16 *q_hi, *q_lo; // operand for the first GEMM
+    const float *metric, *mu;
+    int64_t C;
+    int D, Dp, L;
+    float eps, half_eps;
+    bk_rng rng;
+    float *draws, *logp;
+    int32_t* accept;
+};
+
+// One warp per chain, lane-strided blocks of 4 elements (the Philox block
+// mapping); VEC = rows are 16-byte aligned and D % 4 == 0 -> 128-bit accesses.
+template <bool VEC>
+__device__ __forceinline__ void ld4(const float* p, int e, int D, float (&v)[4]) {
+    if (VEC) {
+        const float4 t = *reinterpret_cast<const float4*>(p + e);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = (e + i < D) ? p[e + i] : 0.f;
+    }
+}
+template <bool VEC>
+__device__ __forceinline__ void st4(float* p, int e, int D, const float (&v)[4]) {
+    if (VEC) {
+        *reinterpret_cast<float4*>(p + e) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (e + i < D) p[e + i] = v[i];
+    }
+}
+template <bool VEC>
+__device__ __forceinline__ void st4_bf16(__nv_bfloat16* p, int e, int D, const __nv_bfloat16 (&v)[4]) {
+    if (VEC) {
+        uint2 u;
+        u.x = (uint32_t)__bfloat16_as_ushort(v[0]) | ((uint32_t)__bfloat16_as_ushort(v[1]) << 16);
+        u.y = (uint32_t)__bfloat16_as_ushort(v[2]) | ((uint32_t)__bfloat16_as_ushort(v[3]) << 16);
+        *reinterpret_cast<uint2*>(p + e) = u;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (e + i < D) p[e + i] = v[i];
+    }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_hmc_begin_tc(HmcTcArgs p, int64_t t, int write_lo) {
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= p.C) return;
+    const int D = p.D;
+    const int64_t off = c * (int64_t)D;
+    float kin = 0.f;
+#pragma unroll 2
+    for (int b = lane; 4 * b < D; b += 32) {
+        const int e = 4 * b;
+        float z[4], g[4], th[4], m[4] = {1.f, 1.f, 1.f, 1.f};
+        ld4<VEC>(p.grad + off, e, D, g);
+        ld4<VEC>(p.theta + off, e, D, th);
+        if (p.metric) ld4<VEC>(p.metric, e, D, m);
+        if (p.rng.mode == BK_RNG_INJECTED)
+            ld4<VEC>(reinterpret_cast<const float*>(p.rng.normals) + (t * p.C + c) * (int64_t)D, e, D, z);
+        else
+            philox_normal4<float>(p.rng.seed, (uint32_t)b, (uint32_t)(p.rng.chain_offset + (uint64_t)c),
+                                  (uint32_t)(p.rng.draw_offset + (uint64_t)t), z);
+        float r[4], q[4];
+        __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (!VEC && e + i >= D) z[i] = 0.f;
+            const float mg = m[i] * g[i];
+            kin = fmaf(z[i], m[i] * z[i], kin);
+            r[i] = z[i] - p.half_eps * mg;    // backward half kick (hmc.py:46)
+            r[i] = r[i] + p.eps * mg;         // first full kick     (hmc.py:48)
+            q[i] = th[i] + p.eps * r[i];
+            hi[i] = __float2bfloat16_rn(q[i]);
+            lo[i] = __float2bfloat16_rn(q[i] - __bfloat162float(hi[i]));
+        }
+        st4<VEC>(p.r + off, e, D, r);
+        st4<VEC>(p.q + off, e, D, q);
+        st4_bf16<VEC>(p.q_hi + c * p.Dp, e, D, hi);
+        if (write_lo) st4_bf16<VEC>(p.q_lo + c * p.Dp, e, D, lo);
+    }
+    kin = warp_sum(kin);
+    if (lane == 0) p.h0[c] = p.lp[c] - 0.5f * kin;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_hmc_end_tc(HmcTcArgs p, int64_t t) {
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= p.C) return;
+    const int D = p.D;
+    const int64_t off = c * (int64_t)D;
+    float kin = 0.f, dot = 0.f;
+#pragma unroll 2
+    for (int b = lane; 4 * b < D; b += 32) {
+        const int e = 4 * b;
+        float g[4], r[4], q[4], m[4] = {1.f, 1.f, 1.f, 1.f}, mu[4] = {0.f, 0.f, 0.f, 0.f};
+        ld4<VEC>(p.gq + off, e, D, g);
+        ld4<VEC>(p.r + off, e, D, r);
+        ld4<VEC>(p.q + off, e, D, q);
+        if (p.metric) ld4<VEC>(p.metric, e, D, m);
+        if (p.mu) ld4<VEC>(p.mu, e, D, mu);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float rf = r[i] + p.half_eps * (m[i] * g[i]);   // forward half kick (hmc.py:52)
+            kin = fmaf(rf, m[i] * rf, kin);
+            dot = fmaf(q[i] - mu[i], g[i], dot);                  // log p(q) = 0.5 (q-mu).g
+        }
+    }
+    kin = warp_sum(kin);
+    dot = warp_sum(dot);
+    const float lpq = 0.5f * dot;
+    const float h1 = lpq - 0.5f * kin, h0 = p.h0[c];
+    float u;
+    if (p.rng.mode == BK_RNG_INJECTED)
+        u = reinterpret_cast<const float*>(p.rng.uniforms)[(t * p.C + c) * p.rng.n_uniform];
+    else
+        u = philox_uniform<float>(p.rng.seed, 0u, (uint32_t)(p.rng.chain_offset + (uint64_t)c),
+                                  (uint32_t)(p.rng.draw_offset + (uint64_t)t));
+    const bool acc = log_u(u) < h1 - h0;
+    float* dr = p.draws ? p.draws + (t * p.C + c) * (int64_t)D : nullptr;
+#pragma unroll 2
+    for (int b = lane; 4 * b < D; b += 32) {
+        const int e = 4 * b;
+        float v[4];
+        if (acc) {
+            float g[4];
+            ld4<VEC>(p.q + off, e, D, v);
+            ld4<VEC>(p.gq + off, e, D, g);
+            st4<VEC>(p.theta + off, e, D, v);
+            st4<VEC>(p.grad + off, e, D, g);
+        } else if (dr) {
+            ld4<VEC>(p.theta + off, e, D, v);
+        }
+        if (dr) st4<VEC>(dr, e, D, v);
+    }
+    if (lane == 0) {
+        if (acc) p.lp[c] = lpq;
+        if (p.logp) p.logp[t * p.C + c] = acc ? h1 : h0;
+        if (p.accept) p.accept[t * p.C + c] = acc ? 1 : 0;
+    }
+}
+
+// ---- host side --------------------------------------------------------------------
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn get_encode() {
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeFn)p;
+    }
+    return fn;
+}
+
+// bf16 row-major [rows, Dp] (pitch Dp), box = [box_rows x 64 k], 128B swizzle
+static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int Dp, int box_rows) {
+    EncodeFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return BK_E_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)Dp, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)Dp * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t el[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, el,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return BK_E_CUDA; }
+    return BK_OK;
+}
+
+static int launch_tc(const Model& m, const StepArgs& a, const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo,
+                     cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        BK_CUDA(cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr = true;
+    }
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        BK_CUDA(cudaGetDevice(&dev));
+        BK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    CUtensorMap mA0, mA1, mB0, mB1;
+    int rc;
+    if ((rc = make_map(&mA0, m.P_hi, m.Dp, (int)m.Dp, BM))) return rc;
+    if ((rc = make_map(&mA1, m.P_lo, m.Dp, (int)m.Dp, BM))) return rc;
+    if ((rc = make_map(&mB0, b_hi, a.C, (int)m.Dp, BN))) return rc;
+    if ((rc = make_map(&mB1, b_lo ? b_lo : b_hi, a.C, (int)m.Dp, BN))) return rc;
+    const int64_t tiles = a.n_tiles * a.m_tiles;
+    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+    prof_begin(BK_PROF_GRAD, st);
+    k_dense_tc<<<grid, THREADS, SMEM_BYTES, st>>>(mA0, mA1, mB0, mB1, a);
+    prof_end(BK_PROF_GRAD, st);
+    BK_LAUNCH_CHECK();
+    return BK_OK;
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------
+bool dense_tc_enabled(const Model& m) {
+    const char* e = getenv("BK_DISABLE_TC");
+    if (e && e[0] == '1') return false;
+    return m.d.kind == BK_MODEL_DENSE_PREC_GAUSS && m.d.dtype == BK_F32 && m.P_hi != nullptr;
+}
+
+size_t dense_tc_model_ws_bytes(const bk_model_desc& d) {
+    if (d.kind != BK_MODEL_DENSE_PREC_GAUSS || d.dtype != BK_F32) return 0;
+    const size_t Dp = align_up((size_t)d.dims, 128);
+    return 2 * align_up(Dp * Dp * 2, 256) + align_up((size_t)d.dims * 4, 256) + 1024;
+}
+
+int dense_tc_prepare(Model& m, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (m.d.kind != BK_MODEL_DENSE_PREC_GAUSS || m.d.dtype != BK_F32) return BK_OK;
+    const int D = (int)m.d.dims;
+    m.Dp = (int64_t)align_up((size_t)D, 128);
+    Arena ar(ws, ws_bytes);
+    m.P_hi = ar.take<__nv_bfloat16>((size_t)m.Dp * m.Dp);
+    m.P_lo = ar.take<__nv_bfloat16>((size_t)m.Dp * m.Dp);
+    m.Pmu = m.d.mu ? (void*)ar.take<float>(D) : nullptr;
+    if (!ar.ok()) {
+        m.P_hi = m.P_lo = nullptr;
+        m.Pmu = nullptr;
+        set_error("bk_model_create: workspace too small for the tensor-core operands (%zu < %zu)", ws_bytes,
+                  ar.off);
+        return BK_E_WORKSPACE;
+    }
+    const int64_t n = m.Dp * m.Dp;
+    tc::k_split_matrix<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float*)m.d.P, D, (int)m.Dp, m.P_hi,
+                                                                     m.P_lo);
+    BK_LAUNCH_CHECK();
+    if (m.Pmu) {
+        tc::k_pmu<<<(unsigned)(((int64_t)D * 32 + 255) / 256), 256, 0, st>>>((const float*)m.d.P,
+                                                                             (const float*)m.d.mu, D,
+                                                                             (float*)m.Pmu);
+        BK_LAUNCH_CHECK();
+    }
+    return BK_OK;
+}
+
+size_t dense_tc_hmc_ws_bytes(const Model& m, int64_t C) {
+    const size_t n = (size_t)C * m.d.dims, nb = (size_t)C * m.Dp;
+    // q, r, gq fp32; h0; q_hi x2, q_lo bf16; SIMT eval scratch for the cache refresh
+    return 3 * align_up(n * 4, 256) + align_up((size_t)C * 4, 256) + 3 * align_up(nb * 2, 256) +
+           model_eval_ws_bytes(m, C) + 2048;
+}
+
+// gradient of the dense plugin on tensor cores (3-pass split): theta [C,D] -> grad [C,D]
+int dense_tc_grad(const Model& m, const float* theta, int64_t C, float* grad, void* ws, size_t ws_bytes,
+                  cudaStream_t st) {
+    Arena ar(ws, ws_bytes);
+    const size_t nb = (size_t)C * m.Dp;
+    __nv_bfloat16* hi = ar.take<__nv_bfloat16>(nb);
+    __nv_bfloat16* lo = ar.take<__nv_bfloat16>(nb);
+    if (!ar.ok()) { set_error("dense_tc_grad: workspace too small"); return BK_E_WORKSPACE; }
+    const int D = (int)m.d.dims;
+    BK_CUDA(cudaMemsetAsync(hi, 0, nb * 2, st));
+    BK_CUDA(cudaMemsetAsync(lo, 0, nb * 2, st));
+    tc::k_split_rows<<<(unsigned)((C * D + 255) / 256), 256, 0, st>>>(theta, C, D, (int)m.Dp, hi, lo);
+    BK_LAUNCH_CHECK();
+    tc::StepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mode = TC_MODE_GRAD; a.n_pass = 3; a.C = C; a.D = D; a.Dp = (int)m.Dp;
+    a.m_tiles = (int)(m.Dp / tc::BM); a.n_tiles = (C + tc::BN - 1) / tc::BN; a.kblocks = (int)(m.Dp / tc::BK);
+    a.cvec = (const float*)m.Pmu; a.g_out = grad;
+    return tc::launch_tc(m, a, hi, lo, st);
+}
+
+int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* cache_valid, int64_t C,
+                 double eps, int L, const float* metric, int64_t n_draws, const bk_rng* rng,
+                 const bk_draw_out& out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const int D = (int)m.d.dims;
+    const size_t n = (size_t)C * D, nb = (size_t)C * m.Dp;
+    Arena ar(ws, ws_bytes);
+    float* q = ar.take<float>(n);
+    float* r = ar.take<float>(n);
+    float* gq = ar.take<float>(n);
+    float* h0 = ar.take<float>(C);
+    __nv_bfloat16* qhi[2] = {ar.take<__nv_bfloat16>(nb), ar.take<__nv_bfloat16>(nb)};
+    __nv_bfloat16* qlo = ar.take<__nv_bfloat16>(nb);
+    const size_t ebytes = model_eval_ws_bytes(m, C);
+    void* ews = ar.take<char>(ebytes);
+    if (!ar.ok()) {
+        set_error("bk_hmc_diag_sample: workspace too small (need %zu bytes, got %zu)", ar.off, ws_bytes);
+        return BK_E_WORKSPACE;
+    }
+    int rc;
+    if (!cache_valid || !*cache_valid) {
+        rc = model_eval(m, theta, C, lp, grad, ews, ebytes, st);   // exact fp32 CUDA-core evaluation
+        if (rc) return rc;
+        if (cache_valid) *cache_valid = 1;
+    }
+    // pad columns [D, Dp) of the bf16 operands must be zero (they multiply P's zero padding)
+    if (m.Dp != D) {
+        BK_CUDA(cudaMemsetAsync(qhi[0], 0, nb * 2, st));
+        BK_CUDA(cudaMemsetAsync(qhi[1], 0, nb * 2, st));
+        BK_CUDA(cudaMemsetAsync(qlo, 0, nb * 2, st));
+    }
+    tc::HmcTcArgs h;
+    memset(&h, 0, sizeof(h));
+    h.theta = theta; h.lp = lp; h.grad = grad; h.q = q; h.r = r; h.gq = gq; h.h0 = h0;
+    h.metric = metric; h.mu = (const float*)m.d.mu; h.C = C; h.D = D; h.Dp = (int)m.Dp; h.L = L;
+    h.eps = (float)eps; h.half_eps = (float)(0.5 * eps); h.rng = *rng;
+    h.draws = (float*)out.draws; h.logp = (float*)out.logp; h.accept = out.accept;
+    tc::StepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.C = C; a.D = D; a.Dp = (int)m.Dp;
+    a.m_tiles = (int)(m.Dp / tc::BM); a.n_tiles = (C + tc::BN - 1) / tc::BN; a.kblocks = (int)(m.Dp / tc::BK);
+    a.eps = (float)eps; a.metric = metric; a.cvec = (const float*)m.Pmu; a.r = r; a.q = q; a.g_out = gq;
+    const unsigned wblocks = (unsigned)((C * 32 + 255) / 256);
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool vec = D % 4 == 0 && al16(theta) && al16(grad) && al16(metric) && al16(m.d.mu) &&
+                     al16(out.draws) && (rng->mode != BK_RNG_INJECTED || al16(rng->normals));
+    for (int64_t t = 0; t < n_draws; ++t) {
+        h.q_hi = qhi[0]; h.q_lo = qlo;
+        if (vec) tc::k_hmc_begin_tc<true><<<wblocks, 256, 0, st>>>(h, t, L == 1 ? 1 : 0);
+        else tc::k_hmc_begin_tc<false><<<wblocks, 256, 0, st>>>(h, t, L == 1 ? 1 : 0);
+        BK_LAUNCH_CHECK();
+        int cur = 0;
+        for (int s = 1; s < L; ++s) {   // fused gradient + kick + drift, bf16 operands
+            a.mode = TC_MODE_STEP; a.n_pass = 1;
+            a.q_hi_next = qhi[cur ^ 1];
+            a.q_lo_next = (s == L - 1) ? qlo : nullptr;
+            rc = tc::launch_tc(m, a, qhi[cur], nullptr, st);
+            if (rc) return rc;
+            cur ^= 1;
+        }
+        // endpoint gradient with the 3-pass split: enters the Hamiltonian and the cache
+        a.mode = TC_MODE_GRAD; a.n_pass = 3; a.q_hi_next = nullptr; a.q_lo_next = nullptr;
+        rc = tc::launch_tc(m, a, qhi[cur], qlo, st);
+        if (rc) return rc;
+        if (vec) tc::k_hmc_end_tc<true><<<wblocks, 256, 0, st>>>(h, t);
+        else tc::k_hmc_end_tc<false><<<wblocks, 256, 0, st>>>(h, t);
+        BK_LAUNCH_CHECK();
+    }
+    return BK_OK;
+}
+
+}  // namespace bk

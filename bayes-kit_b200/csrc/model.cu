@@ -8,6 +8,7 @@
 #include <mutex>
 #include <unordered_map>
 
+#include "dense_tc.h"
 #include "model.h"
 
 namespace bk {
@@ -201,6 +202,19 @@ static int eval_t(const Model& m, const T* theta, int64_t C, T* lp, T* grad, voi
                     return BK_E_WORKSPACE;
                 }
             }
+            if constexpr (sizeof(T) == 4) {
+                if (dense_tc_enabled(m)) {  // tensor cores, 3-pass bf16 split (~2^-16 relative)
+                    Arena ar2(ws, ws_bytes);
+                    if (!grad) ar2.take<T>((size_t)C * D);
+                    char* tws = ar2.take<char>(0);
+                    int rc = dense_tc_grad(m, (const float*)theta, C, (float*)g, tws,
+                                           ws_bytes > ar2.off ? ws_bytes - ar2.off : 0, st);
+                    if (rc) return rc;
+                    k_dense_lp<T><<<wblocks, 256, 0, st>>>(theta, (const T*)m.d.mu, g, C, D, lp);
+                    BK_LAUNCH_CHECK();
+                    return BK_OK;
+                }
+            }
             dim3 grid((D + 63) / 64, (unsigned)((C + 63) / 64));
             prof_begin(BK_PROF_GRAD, st);
             k_dense_grad<T><<<grid, 256, 0, st>>>(theta, (const T*)m.d.mu, (const T*)m.d.P, C, D, g);
@@ -217,8 +231,11 @@ static int eval_t(const Model& m, const T* theta, int64_t C, T* lp, T* grad, voi
 }
 
 size_t model_eval_ws_bytes(const Model& m, int64_t C) {
-    if (m.d.kind == BK_MODEL_DENSE_PREC_GAUSS)
-        return align_up((size_t)C * m.d.dims * (m.d.dtype == BK_F64 ? 8 : 4), 256) + 256;
+    if (m.d.kind == BK_MODEL_DENSE_PREC_GAUSS) {
+        size_t n = align_up((size_t)C * m.d.dims * (m.d.dtype == BK_F64 ? 8 : 4), 256) + 256;
+        if (dense_tc_enabled(m)) n += 2 * align_up((size_t)C * m.Dp * 2, 256) + 512;  // bf16 hi/lo
+        return n;
+    }
     return 0;
 }
 
@@ -237,12 +254,11 @@ extern "C" {
 
 size_t bk_model_workspace_bytes(const bk_model_desc* desc) {
     if (!desc) return 0;
-    return 256;  // derived operands are added by the tcgen05 path
+    return 256 + dense_tc_model_ws_bytes(*desc);  // bf16 splits of P, P*mu
 }
 
 int bk_model_create(const bk_model_desc* desc, void* ws, size_t ws_bytes, void* stream,
                     uint64_t* handle_out) {
-    (void)ws; (void)ws_bytes; (void)stream;
     BK_CHECK_ARG(desc && handle_out, "bk_model_create: null argument");
     BK_CHECK_ARG(desc->dtype == BK_F32 || desc->dtype == BK_F64, "bk_model_create: bad dtype %d",
                  desc->dtype);
@@ -272,6 +288,10 @@ int bk_model_create(const bk_model_desc* desc, void* ws, size_t ws_bytes, void* 
     Model m;
     m.d = *desc;
     if (m.d.kind != BK_MODEL_ISO_GAUSS) m.d.sigma = 1.0;
+    if (ws && ws_bytes >= dense_tc_model_ws_bytes(*desc) && dense_tc_model_ws_bytes(*desc) > 0) {
+        int rc = dense_tc_prepare(m, ws, ws_bytes, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
     std::lock_guard<std::mutex> lk(g_mu);
     uint64_t h = g_next++;
     g_models[h] = m;

@@ -30,7 +30,8 @@ sys.path.insert(0, ROOT)
 
 D = 1000
 L = 10
-EPS = 0.2            # accept ~0.85-0.9 on c2 (tuned with the oracle)
+EPS = 0.1            # eps*L = 1.0 < pi/sqrt(lambda_max): no fixed-length-HMC resonance on c2
+                     # (eps = 0.2 gives accept 0.9 but omega*T crosses pi -> non-ergodic modes)
 CHAINS_PER_GPU = 65536
 METRIC = "hmc_chain_steps_per_s"
 UNIT = "chain-steps/s"
