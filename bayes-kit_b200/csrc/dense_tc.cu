@@ -130,6 +130,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Internal fp32 work arrays (r, q, endpoint gradient) are TILE-BLOCKED to match the
+// epilogue's access pattern: element (chain c, dim d) lives at
+//   ((c / BN) * m_tiles + d / BM) * (BN * BM) + (c % BN) * BM + (d % BM)
+// so the 256 x 128 patch a CTA updates is one contiguous 128 KB run (DRAM-page
+// friendly streaming instead of 128-byte pieces at a 4000-byte stride).
+__host__ __device__ __forceinline__ int64_t blk_index(int64_t c, int d, int m_tiles) {
+    return (((c / BN) * m_tiles + (d / BM)) * (int64_t)(BN * BM)) + (c % BN) * BM + (d % BM);
+}
+
 struct StepArgs {
     int mode;          // TC_MODE_STEP | TC_MODE_GRAD
     int n_pass;        // 1 (bf16) or 3 (bf16x3 split)
@@ -141,11 +150,12 @@ struct StepArgs {
     float eps;
     const float* metric;  // [D] or NULL
     const float* cvec;    // [D] P*mu or NULL
-    float* r;             // [C, D]  (STEP: in/out)
-    float* q;             // [C, D]  (STEP: in/out)
+    float* r;             // tile-blocked (STEP: in/out)
+    float* q;             // tile-blocked (STEP: in/out)
     __nv_bfloat16* q_hi_next;  // [C, Dp] (STEP)
     __nv_bfloat16* q_lo_next;  // [C, Dp] or NULL
-    float* g_out;         // [C, D]  (GRAD)
+    float* g_out;         // [C, D] row-major, or tile-blocked when g_blocked
+    int g_blocked;
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -239,8 +249,8 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         // (issued before the accumulator is even ready), so ~64 KB per SM stay
         // outstanding and the HBM latency is covered.
         const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;
-        constexpr int NCH = BN / 32 / 2;
+        const int half = (warp - 2) >> 2;                  // column slice of this warp
+        constexpr int NCH = BN / 32 / (EPI_WARPS / 4);     // 32-chain groups per warp
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -264,21 +274,23 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int64_t c = c0 + j;
-                        if (d_ok && c < a.C) a.g_out[c * a.D + d] = cv - __uint_as_float(v[j]);
+                        if (d_ok && c < a.C)
+                            a.g_out[a.g_blocked ? blk_index(c, d, a.m_tiles) : c * a.D + d] =
+                                cv - __uint_as_float(v[j]);
                     }
                 }
             } else {
                 // chunks of CW chains; two chunks of r/q loads stay in flight ahead of the math
                 constexpr int CW = 16, NC = NCH * 32 / CW;
                 const bool full_tile = d_ok && cbase + NCH * 32 <= a.C;   // no per-element bounds
-                const int64_t e0 = cbase * a.D + d;
+                const int64_t e0 = blk_index(cbase, d, a.m_tiles);
                 const float* rp = a.r + e0;
                 const float* qp = a.q + e0;
                 float* rw = a.r + e0;
                 float* qw = a.q + e0;
                 __nv_bfloat16* hw = a.q_hi_next + cbase * a.Dp + d;
                 __nv_bfloat16* lw = a.q_lo_next ? a.q_lo_next + cbase * a.Dp + d : nullptr;
-                const int D = a.D, Dp = a.Dp;
+                const int D = BM, Dp = a.Dp;   // r/q chain stride inside a blocked tile = BM
                 const float eps = a.eps;
                 auto load = [&](int ch, float (&rb)[CW], float (&qb)[CW]) {
                     const int64_t o = (int64_t)ch * CW * D;
@@ -391,7 +403,7 @@ struct HmcTcArgs {
     __nv_bfloat16 *q_hi, *q_lo; // operand for the first GEMM
     const float *metric, *mu;
     int64_t C;
-    int D, Dp, L;
+    int D, Dp, L, m_tiles;
     float eps, half_eps;
     bk_rng rng;
     float *draws, *logp;
@@ -467,8 +479,9 @@ __global__ void __launch_bounds__(256) k_hmc_begin_tc(HmcTcArgs p, int64_t t, in
             hi[i] = __float2bfloat16_rn(q[i]);
             lo[i] = __float2bfloat16_rn(q[i] - __bfloat162float(hi[i]));
         }
-        st4<VEC>(p.r + off, e, D, r);
-        st4<VEC>(p.q + off, e, D, q);
+        const int64_t bo = blk_index(c, e, p.m_tiles);   // r, q are tile-blocked
+        st4<true>(p.r + bo, 0, 4, r);
+        st4<true>(p.q + bo, 0, 4, q);
         st4_bf16<VEC>(p.q_hi + c * p.Dp, e, D, hi);
         if (write_lo) st4_bf16<VEC>(p.q_lo + c * p.Dp, e, D, lo);
     }
@@ -488,13 +501,15 @@ __global__ void __launch_bounds__(256) k_hmc_end_tc(HmcTcArgs p, int64_t t) {
     for (int b = lane; 4 * b < D; b += 32) {
         const int e = 4 * b;
         float g[4], r[4], q[4], m[4] = {1.f, 1.f, 1.f, 1.f}, mu[4] = {0.f, 0.f, 0.f, 0.f};
-        ld4<VEC>(p.gq + off, e, D, g);
-        ld4<VEC>(p.r + off, e, D, r);
-        ld4<VEC>(p.q + off, e, D, q);
+        const int64_t bo = blk_index(c, e, p.m_tiles);   // gq, r, q are tile-blocked
+        ld4<true>(p.gq + bo, 0, 4, g);
+        ld4<true>(p.r + bo, 0, 4, r);
+        ld4<true>(p.q + bo, 0, 4, q);
         if (p.metric) ld4<VEC>(p.metric, e, D, m);
         if (p.mu) ld4<VEC>(p.mu, e, D, mu);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+            if (e + i >= D) break;                                // blocked arrays carry pad dims
             const float rf = r[i] + p.half_eps * (m[i] * g[i]);   // forward half kick (hmc.py:52)
             kin = fmaf(rf, m[i] * rf, kin);
             dot = fmaf(q[i] - mu[i], g[i], dot);                  // log p(q) = 0.5 (q-mu).g
@@ -518,8 +533,9 @@ __global__ void __launch_bounds__(256) k_hmc_end_tc(HmcTcArgs p, int64_t t) {
         float v[4];
         if (acc) {
             float g[4];
-            ld4<VEC>(p.q + off, e, D, v);
-            ld4<VEC>(p.gq + off, e, D, g);
+            const int64_t bo = blk_index(c, e, p.m_tiles);
+            ld4<true>(p.q + bo, 0, 4, v);
+            ld4<true>(p.gq + bo, 0, 4, g);
             st4<VEC>(p.theta + off, e, D, v);
             st4<VEC>(p.grad + off, e, D, g);
         } else if (dr) {
@@ -638,8 +654,9 @@ int dense_tc_prepare(Model& m, void* ws, size_t ws_bytes, cudaStream_t st) {
 }
 
 size_t dense_tc_hmc_ws_bytes(const Model& m, int64_t C) {
-    const size_t n = (size_t)C * m.d.dims, nb = (size_t)C * m.Dp;
-    // q, r, gq fp32; h0; q_hi x2, q_lo bf16; SIMT eval scratch for the cache refresh
+    const size_t nb = (size_t)C * m.Dp;
+    const size_t n = (size_t)align_up((size_t)C, tc::BN) * m.Dp;   // tile-blocked, padded
+    // q, r, gq fp32; h0; q_hi x2, q_lo bf16; eval scratch for the cache refresh
     return 3 * align_up(n * 4, 256) + align_up((size_t)C * 4, 256) + 3 * align_up(nb * 2, 256) +
            model_eval_ws_bytes(m, C) + 2048;
 }
@@ -669,7 +686,8 @@ int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* 
                  double eps, int L, const float* metric, int64_t n_draws, const bk_rng* rng,
                  const bk_draw_out& out, void* ws, size_t ws_bytes, cudaStream_t st) {
     const int D = (int)m.d.dims;
-    const size_t n = (size_t)C * D, nb = (size_t)C * m.Dp;
+    const size_t nb = (size_t)C * m.Dp;
+    const size_t n = (size_t)align_up((size_t)C, tc::BN) * m.Dp;   // tile-blocked, padded
     Arena ar(ws, ws_bytes);
     float* q = ar.take<float>(n);
     float* r = ar.take<float>(n);
@@ -699,6 +717,7 @@ int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* 
     memset(&h, 0, sizeof(h));
     h.theta = theta; h.lp = lp; h.grad = grad; h.q = q; h.r = r; h.gq = gq; h.h0 = h0;
     h.metric = metric; h.mu = (const float*)m.d.mu; h.C = C; h.D = D; h.Dp = (int)m.Dp; h.L = L;
+    h.m_tiles = (int)(m.Dp / tc::BM);
     h.eps = (float)eps; h.half_eps = (float)(0.5 * eps); h.rng = *rng;
     h.draws = (float*)out.draws; h.logp = (float*)out.logp; h.accept = out.accept;
     tc::StepArgs a;
@@ -706,6 +725,7 @@ int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* 
     a.C = C; a.D = D; a.Dp = (int)m.Dp;
     a.m_tiles = (int)(m.Dp / tc::BM); a.n_tiles = (C + tc::BN - 1) / tc::BN; a.kblocks = (int)(m.Dp / tc::BK);
     a.eps = (float)eps; a.metric = metric; a.cvec = (const float*)m.Pmu; a.r = r; a.q = q; a.g_out = gq;
+    a.g_blocked = 1;
     const unsigned wblocks = (unsigned)((C * 32 + 255) / 256);
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     const bool vec = D % 4 == 0 && al16(theta) && al16(grad) && al16(metric) && al16(m.d.mu) &&
