@@ -11,23 +11,14 @@
 // consume lags up to the first negative pair (iat.py:37-43), so the fast path
 // computes lag pairs on demand and stops there; bk_autocorr uses the direct
 // sum for short series and the four-step FFT (fft_autocorr.cu) for long ones.
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "diag.h"
 
 namespace bk {
 
 constexpr int ACF_THREADS = 256;
 constexpr int ACF_LAGS = 8;  // lags evaluated per block-wide round
-
-struct SeriesView {
-    const void* x;
-    int dtype;
-    int64_t n_series, N, n_inner, ostride, istride, dstride;
-    __device__ __forceinline__ double at(int64_t s, int64_t t) const {
-        int64_t i = (s / n_inner) * ostride + (s % n_inner) * istride + t * dstride;
-        return dtype == BK_F64 ? reinterpret_cast<const double*>(x)[i]
-                               : (double)reinterpret_cast<const float*>(x)[i];
-    }
-};
 
 // ---- moments -------------------------------------------------------------------
 // one-pass shifted sums (shift = first draw) in fp64
@@ -218,8 +209,8 @@ static SeriesView view_of(const void* x, int32_t dtype, const bk_series_layout* 
 extern "C" {
 
 size_t bk_autocorr_workspace_bytes(int64_t n_series, int64_t N) {
-    (void)n_series; (void)N;
-    return 256;
+    if (n_series <= 0 || N < 2) return 256;
+    return acf_fft_ws_bytes(n_series, N);
 }
 
 int bk_chain_moments(const void* x, int32_t dtype, const bk_series_layout* layout, double* mean_out,
@@ -274,13 +265,17 @@ static int acf_launch(const SeriesView& v, int mode, int estimator, double* acf,
 
 int bk_autocorr(const void* x, int32_t dtype, const bk_series_layout* layout, double* out, void* ws,
                 size_t ws_bytes, void* stream) {
-    (void)ws; (void)ws_bytes;
     int rc = check_series(x, dtype, layout, "bk_autocorr");
     if (rc) return rc;
     BK_CHECK_ARG(layout->n_draws >= 2, "autocorr requires len(chain) >= 2, but len(chain)=%lld",
                  (long long)layout->n_draws);
     BK_CHECK_ARG(out, "bk_autocorr: out is required");
     if (layout->n_series == 0) return BK_OK;
+    // short series: O(N^2) direct sums are cheaper than the transform; BK_ACF=direct|fft overrides
+    const char* e = getenv("BK_ACF");
+    const bool use_fft = e ? (e[0] == 'f') : layout->n_draws > 256;
+    if (use_fft)
+        return acf_fft_launch(view_of(x, dtype, layout), out, ws, ws_bytes, (cudaStream_t)stream);
     return acf_launch(view_of(x, dtype, layout), 0, 0, out, nullptr, nullptr, (cudaStream_t)stream);
 }
 

@@ -224,13 +224,16 @@ static int eval_t(const Model& m, const T* theta, int64_t C, T* lp, T* grad, voi
             BK_LAUNCH_CHECK();
             return BK_OK;
         }
+        case BK_MODEL_HIER_LOGREG:
+            return hlr_eval(m, theta, C, lp, grad, ws, ws_bytes, st);
         default:
-            set_error("model kind %d has no device evaluator yet", m.d.kind);
+            set_error("model kind %d has no device evaluator", m.d.kind);
             return BK_E_UNSUPPORTED;
     }
 }
 
 size_t model_eval_ws_bytes(const Model& m, int64_t C) {
+    if (m.d.kind == BK_MODEL_HIER_LOGREG) return hlr_eval_ws_bytes(m, C);
     if (m.d.kind == BK_MODEL_DENSE_PREC_GAUSS) {
         size_t n = align_up((size_t)C * m.d.dims * (m.d.dtype == BK_F64 ? 8 : 4), 256) + 256;
         if (dense_tc_enabled(m)) n += 2 * align_up((size_t)C * m.Dp * 2, 256) + 512;  // bf16 hi/lo
@@ -280,6 +283,7 @@ int bk_model_create(const bk_model_desc* desc, void* ws, size_t ws_bytes, void* 
             break;
         case BK_MODEL_HIER_LOGREG:
             BK_CHECK_ARG(desc->X && desc->y && desc->n_obs > 0, "HIER_LOGREG: X, y, n_obs required");
+            BK_CHECK_ARG(desc->dims >= 3, "HIER_LOGREG: dims = Dx + 2 must be >= 3");
             break;
         default:
             set_error("bk_model_create: unknown kind %d", desc->kind);

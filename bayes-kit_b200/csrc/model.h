@@ -26,4 +26,9 @@ size_t model_eval_ws_bytes(const Model& m, int64_t C);
 int model_eval(const Model& m, const void* theta, int64_t C, void* lp, void* grad, void* ws,
                size_t ws_bytes, cudaStream_t st);
 
+// hierarchical logistic regression evaluator (logreg.cu)
+size_t hlr_eval_ws_bytes(const Model& m, int64_t C);
+int hlr_eval(const Model& m, const void* theta, int64_t C, void* lp, void* grad, void* ws, size_t ws_bytes,
+             cudaStream_t st);
+
 }  // namespace bk

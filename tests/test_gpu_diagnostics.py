@@ -100,3 +100,18 @@ def test_exceptions(bk):
     for bad in ([], [[1.01, 1.2, 1.3, 1.4]], [[1, 2, 3], [4], [5, 6, 7, 8, 9]]):
         with pytest.raises(ValueError):
             bk.rhat(bad)
+
+
+@pytest.mark.parametrize("mode", ["direct", "fft"])
+def test_autocorr_both_paths(bk, mode, monkeypatch):
+    """The direct-sum and the hand-written FFT kernels are the same estimator."""
+    monkeypatch.setenv("BK_ACF", mode)
+    z = golden("diagnostics")
+    for tag in ("n37", "n1000") + (("n10000",) if mode == "fft" else ()):
+        np.testing.assert_allclose(np_(bk.autocorr(z["x_" + tag])), z["autocorr_" + tag], **TOL)
+    rng = np.random.default_rng(4)
+    for n in (2, 3, 5, 64, 257, 4097):   # FFT sizes 4 .. 16384 (both sides of the in-smem limit)
+        x = np.stack([od.sample_ar1(0.7, n, rng) for _ in range(3)])
+        np.testing.assert_allclose(np_(bk.autocorr(x)), od.autocorr_batch(x), **TOL)
+    x32 = torch.as_tensor(od.sample_ar1(0.5, 5000, rng), dtype=torch.float32, device="cuda")
+    np.testing.assert_allclose(np_(bk.autocorr(x32)), od.autocorr(np_(x32).astype(np.float64)), **TOL)
