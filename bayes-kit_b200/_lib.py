@@ -17,7 +17,7 @@ MODEL_ISO, MODEL_DIAG, MODEL_DENSE, MODEL_HLR, MODEL_GPL = range(5)
 RNG_PHILOX, RNG_INJECTED = 0, 1
 RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC = 0, 1
 IAT_IPSE, IAT_IMSE = 0, 1
-PROF_GRAD, PROF_SAMPLER = 0, 1
+PROF_GRAD, PROF_SAMPLER, PROF_STEP = 0, 1, 2
 
 vp, i32, i64, u64, f64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double, C.c_size_t
 
@@ -76,6 +76,8 @@ _SIGNATURES = {
     "bk_smc_weight_stats": (C.c_int, [vp, i64, i32, i32, vp, vp, sz, vp]),
     "bk_smc_resample_indices": (C.c_int, [vp, i64, i32, i32, f64, f64, vp, C.POINTER(Rng), i64, i64,
                                           vp, vp, vp, sz, vp]),
+    "bk_smc_resample_indices_dev": (C.c_int, [vp, i64, i32, i32, vp, vp, C.POINTER(Rng), i64, i64, vp, vp,
+                                              vp, sz, vp]),
     "bk_gather_rows": (C.c_int, [vp, vp, i64, i64, i32, vp, vp]),
     "bk_autocorr_workspace_bytes": (sz, [i64, i64]),
     "bk_autocorr": (C.c_int, [vp, i32, C.POINTER(SeriesLayout), vp, vp, sz, vp]),

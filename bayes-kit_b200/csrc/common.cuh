@@ -147,10 +147,12 @@ __device__ __forceinline__ void philox_normal4<float>(uint64_t seed, uint32_t bl
                                                       uint32_t draw, float (&z)[4]) {
     uint32_t r[4];
     Philox::gen(seed, block, TAG_NORMAL, chain, draw, r);
-    float r0 = sqrtf(-2.0f * logf(u01(r[0]))), r1 = sqrtf(-2.0f * logf(u01(r[2])));
+    // Box-Muller on the SFU: __logf / __sincosf have ~2^-21 absolute error on these
+    // ranges (angle folded into [-pi, pi)) -- far below the fp32 sampling noise.
+    float r0 = sqrtf(-2.0f * __logf(u01(r[0]))), r1 = sqrtf(-2.0f * __logf(u01(r[2])));
     float s0, c0, s1, c1;
-    sincospif(2.0f * u01(r[1]), &s0, &c0);
-    sincospif(2.0f * u01(r[3]), &s1, &c1);
+    __sincosf(6.2831853071795865f * (u01(r[1]) - 0.5f), &s0, &c0);
+    __sincosf(6.2831853071795865f * (u01(r[3]) - 0.5f), &s1, &c1);
     z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
 }
 template <>

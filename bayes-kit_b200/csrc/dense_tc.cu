@@ -139,6 +139,14 @@ __host__ __device__ __forceinline__ int64_t blk_index(int64_t c, int d, int m_ti
     return (((c / BN) * m_tiles + (d / BM)) * (int64_t)(BN * BM)) + (c % BN) * BM + (d % BM);
 }
 
+// bf16 MMA operands are stored BOX-BLOCKED: one TMA box ([rows_per_box x 64 k], 128 B per
+// row) is one contiguous run, boxes ordered [row_tile][k_block]:
+//   element (row, k) at (((row / RB) * kblocks + k / 64) * RB + row % RB) * 64 + k % 64
+// -> every TMA load is a contiguous 16/32 KB read and the epilogue fills whole boxes.
+__host__ __device__ __forceinline__ int64_t box_index(int64_t row, int k, int kblocks, int RB) {
+    return (((row / RB) * kblocks + (k / BK)) * RB + (row % RB)) * (int64_t)BK + (k % BK);
+}
+
 struct StepArgs {
     int mode;          // TC_MODE_STEP | TC_MODE_GRAD
     int n_pass;        // 1 (bf16) or 3 (bf16x3 split)
@@ -210,8 +218,9 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                     const CUtensorMap* mb = pass == 1 ? &mapB1 : &mapB0;
                     mbar_wait(empty(stage), phase ^ 1u);
                     mbar_expect_tx(full(stage), A_BYTES + B_BYTES);
-                    tma_load_2d(sA + stage * A_BYTES, ma, full(stage), kb * BK, m_tile * BM);
-                    tma_load_2d(sB + stage * B_BYTES, mb, full(stage), kb * BK, (int)(n_tile * BN));
+                    tma_load_2d(sA + stage * A_BYTES, ma, full(stage), 0, (m_tile * a.kblocks + kb) * BM);
+                    tma_load_2d(sB + stage * B_BYTES, mb, full(stage), 0,
+                                (int)((n_tile * a.kblocks + kb) * BN));
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -288,9 +297,10 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                 const float* qp = a.q + e0;
                 float* rw = a.r + e0;
                 float* qw = a.q + e0;
-                __nv_bfloat16* hw = a.q_hi_next + cbase * a.Dp + d;
-                __nv_bfloat16* lw = a.q_lo_next ? a.q_lo_next + cbase * a.Dp + d : nullptr;
-                const int D = BM, Dp = a.Dp;   // r/q chain stride inside a blocked tile = BM
+                const int64_t b0i = box_index(cbase, d, a.kblocks, BN);   // chain stride inside a box = BK
+                __nv_bfloat16* hw = a.q_hi_next + b0i;
+                __nv_bfloat16* lw = a.q_lo_next ? a.q_lo_next + b0i : nullptr;
+                const int D = BM, Dp = BK;     // chain strides inside the blocked fp32 tile / bf16 box
                 const float eps = a.eps;
                 auto load = [&](int ch, float (&rb)[CW], float (&qb)[CW]) {
                     const int64_t o = (int64_t)ch * CW * D;
@@ -369,8 +379,9 @@ __global__ void k_split_matrix(const float* __restrict__ P, int D, int Dp, __nv_
     int r = (int)(i / Dp), c = (int)(i % Dp);
     float v = (r < D && c < D) ? P[(int64_t)r * D + c] : 0.0f;
     __nv_bfloat16 h = __float2bfloat16_rn(v);
-    hi[i] = h;
-    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    const int64_t o = box_index(r, c, Dp / BK, BM);
+    hi[o] = h;
+    lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
 // cvec = P * mu (fp64 accumulate), one warp per row
@@ -392,8 +403,9 @@ __global__ void k_split_rows(const float* __restrict__ x, int64_t C, int D, int 
     int d = (int)(i % D);
     float v = x[i];
     __nv_bfloat16 h = __float2bfloat16_rn(v);
-    hi[c * Dp + d] = h;
-    if (lo) lo[c * Dp + d] = __float2bfloat16_rn(v - __bfloat162float(h));
+    const int64_t o = box_index(c, d, Dp / BK, BN);
+    hi[o] = h;
+    if (lo) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
 // ---- HMC begin / end around the tensor-core steps (fp32) ----------------------------
@@ -482,8 +494,9 @@ __global__ void __launch_bounds__(256) k_hmc_begin_tc(HmcTcArgs p, int64_t t, in
         const int64_t bo = blk_index(c, e, p.m_tiles);   // r, q are tile-blocked
         st4<true>(p.r + bo, 0, 4, r);
         st4<true>(p.q + bo, 0, 4, q);
-        st4_bf16<VEC>(p.q_hi + c * p.Dp, e, D, hi);
-        if (write_lo) st4_bf16<VEC>(p.q_lo + c * p.Dp, e, D, lo);
+        const int64_t xo = box_index(c, e, p.Dp / BK, BN);   // e % 4 == 0: stays inside one box row
+        st4_bf16<true>(p.q_hi + xo, 0, 4, hi);
+        if (write_lo) st4_bf16<true>(p.q_lo + xo, 0, 4, lo);
     }
     kin = warp_sum(kin);
     if (lane == 0) p.h0[c] = p.lp[c] - 0.5f * kin;
@@ -568,11 +581,13 @@ static EncodeFn get_encode() {
 }
 
 // bf16 row-major [rows, Dp] (pitch Dp), box = [box_rows x 64 k], 128B swizzle
+// box-blocked bf16 operand: a [n_boxes * box_rows, 64] matrix with 128-byte rows
 static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int Dp, int box_rows) {
     EncodeFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return BK_E_CUDA; }
-    cuuint64_t dims[2] = {(cuuint64_t)Dp, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)Dp * 2};
+    const int64_t row_tiles = (rows + box_rows - 1) / box_rows;
+    cuuint64_t dims[2] = {(cuuint64_t)BK, (cuuint64_t)(row_tiles * (Dp / BK) * box_rows)};
+    cuuint64_t strides[1] = {(cuuint64_t)BK * 2};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t el[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, el,
@@ -603,9 +618,10 @@ static int launch_tc(const Model& m, const StepArgs& a, const __nv_bfloat16* b_h
     if ((rc = make_map(&mB1, b_lo ? b_lo : b_hi, a.C, (int)m.Dp, BN))) return rc;
     const int64_t tiles = a.n_tiles * a.m_tiles;
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-    prof_begin(BK_PROF_GRAD, st);
+    const int tag = a.mode == TC_MODE_STEP ? BK_PROF_STEP : BK_PROF_GRAD;
+    prof_begin(tag, st);
     k_dense_tc<<<grid, THREADS, SMEM_BYTES, st>>>(mA0, mA1, mB0, mB1, a);
-    prof_end(BK_PROF_GRAD, st);
+    prof_end(tag, st);
     BK_LAUNCH_CHECK();
     return BK_OK;
 }
@@ -654,8 +670,8 @@ int dense_tc_prepare(Model& m, void* ws, size_t ws_bytes, cudaStream_t st) {
 }
 
 size_t dense_tc_hmc_ws_bytes(const Model& m, int64_t C) {
-    const size_t nb = (size_t)C * m.Dp;
     const size_t n = (size_t)align_up((size_t)C, tc::BN) * m.Dp;   // tile-blocked, padded
+    const size_t nb = n;                                           // box-blocked bf16, padded
     // q, r, gq fp32; h0; q_hi x2, q_lo bf16; eval scratch for the cache refresh
     return 3 * align_up(n * 4, 256) + align_up((size_t)C * 4, 256) + 3 * align_up(nb * 2, 256) +
            model_eval_ws_bytes(m, C) + 2048;
@@ -665,7 +681,7 @@ size_t dense_tc_hmc_ws_bytes(const Model& m, int64_t C) {
 int dense_tc_grad(const Model& m, const float* theta, int64_t C, float* grad, void* ws, size_t ws_bytes,
                   cudaStream_t st) {
     Arena ar(ws, ws_bytes);
-    const size_t nb = (size_t)C * m.Dp;
+    const size_t nb = (size_t)align_up((size_t)C, tc::BN) * m.Dp;   // box-blocked, padded chains
     __nv_bfloat16* hi = ar.take<__nv_bfloat16>(nb);
     __nv_bfloat16* lo = ar.take<__nv_bfloat16>(nb);
     if (!ar.ok()) { set_error("dense_tc_grad: workspace too small"); return BK_E_WORKSPACE; }
@@ -686,8 +702,8 @@ int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* 
                  double eps, int L, const float* metric, int64_t n_draws, const bk_rng* rng,
                  const bk_draw_out& out, void* ws, size_t ws_bytes, cudaStream_t st) {
     const int D = (int)m.d.dims;
-    const size_t nb = (size_t)C * m.Dp;
     const size_t n = (size_t)align_up((size_t)C, tc::BN) * m.Dp;   // tile-blocked, padded
+    const size_t nb = n;                                           // box-blocked bf16, padded
     Arena ar(ws, ws_bytes);
     float* q = ar.take<float>(n);
     float* r = ar.take<float>(n);
@@ -707,8 +723,8 @@ int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* 
         if (rc) return rc;
         if (cache_valid) *cache_valid = 1;
     }
-    // pad columns [D, Dp) of the bf16 operands must be zero (they multiply P's zero padding)
-    if (m.Dp != D) {
+    // pad dims [D, Dp) and pad chains of the bf16 operands must be zero / finite
+    if (m.Dp != D || (C % tc::BN) != 0) {
         BK_CUDA(cudaMemsetAsync(qhi[0], 0, nb * 2, st));
         BK_CUDA(cudaMemsetAsync(qhi[1], 0, nb * 2, st));
         BK_CUDA(cudaMemsetAsync(qlo, 0, nb * 2, st));

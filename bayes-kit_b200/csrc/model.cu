@@ -236,7 +236,7 @@ size_t model_eval_ws_bytes(const Model& m, int64_t C) {
     if (m.d.kind == BK_MODEL_HIER_LOGREG) return hlr_eval_ws_bytes(m, C);
     if (m.d.kind == BK_MODEL_DENSE_PREC_GAUSS) {
         size_t n = align_up((size_t)C * m.d.dims * (m.d.dtype == BK_F64 ? 8 : 4), 256) + 256;
-        if (dense_tc_enabled(m)) n += 2 * align_up((size_t)C * m.Dp * 2, 256) + 512;  // bf16 hi/lo
+        if (dense_tc_enabled(m)) n += 2 * align_up(align_up((size_t)C, 256) * m.Dp * 2, 256) + 512;  // bf16 hi/lo
         return n;
     }
     return 0;

@@ -181,9 +181,14 @@ constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 4, SCAN_TILE = SCAN_THREADS * SCA
 template <typename T>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_local(const T* __restrict__ logw, int64_t n,
                                                              double shift, double total,
+                                                             const double* __restrict__ stats, int mode,
                                                              double* __restrict__ cdf,
                                                              double* __restrict__ block_tot) {
     __shared__ double wsum[SCAN_THREADS / 32];
+    if (stats) {  // normaliser produced on device by bk_smc_weight_stats
+        shift = stats[0];
+        total = mode == BK_RESAMPLE_MULTINOMIAL ? stats[1] : 1.0;
+    }
     const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     double v[SCAN_ITEMS];
     double run = 0;
@@ -333,15 +338,15 @@ int bk_smc_weight_stats(const void* logw, int64_t M, int32_t dtype, int32_t mode
     return BK_OK;
 }
 
-int bk_smc_resample_indices(const void* logw, int64_t M, int32_t dtype, int32_t mode, double shift,
-                            double total, const void* uniforms, const bk_rng* rng, int64_t n_points,
-                            int64_t point_offset, int64_t* idx_out, void* cdf_out, void* ws,
-                            size_t ws_bytes, void* stream) {
+static int resample_impl(const void* logw, int64_t M, int32_t dtype, int32_t mode, double shift, double total,
+                         const double* stats, const void* uniforms, const bk_rng* rng, int64_t n_points,
+                         int64_t point_offset, int64_t* idx_out, void* cdf_out, void* ws, size_t ws_bytes,
+                         void* stream) {
     BK_CHECK_ARG(logw && idx_out && M >= 1, "bk_smc_resample_indices: bad argument");
     BK_CHECK_ARG(mode == BK_RESAMPLE_MULTINOMIAL || mode == BK_RESAMPLE_SYSTEMATIC,
                  "bk_smc_resample_indices: bad mode %d", mode);
     BK_CHECK_ARG(uniforms || rng, "bk_smc_resample_indices: need uniforms or rng");
-    BK_CHECK_ARG(total > 0, "bk_smc_resample_indices: total weight must be > 0 (got %g)", total);
+    BK_CHECK_ARG(stats || total > 0, "bk_smc_resample_indices: total weight must be > 0 (got %g)", total);
     BK_CHECK_ARG(n_points >= 0 && point_offset >= 0 && point_offset + n_points <= M,
                  "bk_smc_resample_indices: point range [%lld, %lld) outside [0, %lld)",
                  (long long)point_offset, (long long)(point_offset + n_points), (long long)M);
@@ -354,9 +359,11 @@ int bk_smc_resample_indices(const void* logw, int64_t M, int32_t dtype, int32_t 
     if (!ar.ok()) { set_error("bk_smc_resample_indices: workspace too small"); return BK_E_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == BK_F64)
-        k_scan_local<double><<<nb, SCAN_THREADS, 0, st>>>((const double*)logw, M, shift, total, cdf, btot);
+        k_scan_local<double><<<nb, SCAN_THREADS, 0, st>>>((const double*)logw, M, shift, total, stats, mode,
+                                                           cdf, btot);
     else
-        k_scan_local<float><<<nb, SCAN_THREADS, 0, st>>>((const float*)logw, M, shift, total, cdf, btot);
+        k_scan_local<float><<<nb, SCAN_THREADS, 0, st>>>((const float*)logw, M, shift, total, stats, mode, cdf,
+                                                          btot);
     BK_LAUNCH_CHECK();
     k_scan_blocks<<<1, 32, 0, st>>>(btot, nb, btot + nb);
     BK_LAUNCH_CHECK();
@@ -376,6 +383,23 @@ int bk_smc_resample_indices(const void* logw, int64_t M, int32_t dtype, int32_t 
         BK_LAUNCH_CHECK();
     }
     return BK_OK;
+}
+
+int bk_smc_resample_indices(const void* logw, int64_t M, int32_t dtype, int32_t mode, double shift,
+                            double total, const void* uniforms, const bk_rng* rng, int64_t n_points,
+                            int64_t point_offset, int64_t* idx_out, void* cdf_out, void* ws,
+                            size_t ws_bytes, void* stream) {
+    return resample_impl(logw, M, dtype, mode, shift, total, nullptr, uniforms, rng, n_points, point_offset,
+                         idx_out, cdf_out, ws, ws_bytes, stream);
+}
+
+int bk_smc_resample_indices_dev(const void* logw, int64_t M, int32_t dtype, int32_t mode, const double* stats,
+                                const void* uniforms, const bk_rng* rng, int64_t n_points,
+                                int64_t point_offset, int64_t* idx_out, void* cdf_out, void* ws,
+                                size_t ws_bytes, void* stream) {
+    BK_CHECK_ARG(stats, "bk_smc_resample_indices_dev: stats is required");
+    return resample_impl(logw, M, dtype, mode, 0.0, 1.0, stats, uniforms, rng, n_points, point_offset, idx_out,
+                         cdf_out, ws, ws_bytes, stream);
 }
 
 int bk_gather_rows(const void* src, const int64_t* idx, int64_t M, int64_t D, int32_t dtype, void* out,

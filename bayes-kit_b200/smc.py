@@ -82,10 +82,9 @@ class TemperedLikelihoodSMC:
         if self.D != self._model.dims():
             raise ValueError("sample_initial returned the wrong dimension")
         self._ws = Workspace(self.device)
-        self._stats = torch.empty(3, dtype=torch.float64, device=self.device)
         self.last_indices = None
         self.last_accept = None
-        self.weight_ess = []  # diagnostic only: the reference resamples unconditionally (smc.py:60)
+        self._stats_log = []  # per temperature: device tensor [shift, sum w, sum w^2]
 
     # ---- reference surface -----------------------------------------------------------
     def log_prior(self, theta):
@@ -104,6 +103,15 @@ class TemperedLikelihoodSMC:
 
     def time(self, n: int) -> float:
         return n / self.N
+
+    @property
+    def weight_ess(self):
+        """Importance-weight ESS (sum w)^2 / sum w^2 per temperature taken so far.
+        Diagnostic only: the reference resamples unconditionally (smc.py:60)."""
+        if not self._stats_log:
+            return []
+        s = torch.stack(self._stats_log).cpu()
+        return [float(a * a / b) if b > 0 else float("nan") for _, a, b in s.tolist()]
 
     def transition(self, n: int, normals=None, acc_uniforms=None, res_uniforms=None) -> None:
         """One temperature step (smc.py:46-60).  The optional arrays inject the
@@ -128,11 +136,10 @@ class TemperedLikelihoodSMC:
             thetas_all = D_.all_gather_cat(self.thetas, self._group)  # [M, D]
             Mg = logw_all.shape[0]
             wp, wn = self._ws.get(lib.bk_smc_resample_workspace_bytes(Mg))
+            stats = torch.empty(3, dtype=torch.float64, device=self.device)
             L.check(lib.bk_smc_weight_stats(logw_all.data_ptr(), Mg, L.BK_F32 if self.dtype == torch.float32
-                                            else L.BK_F64, mode, self._stats.data_ptr(), wp, wn, st))
-            stats = self._stats.cpu()  # 3 doubles: shift, sum w, sum w^2
-            shift, total, total2 = float(stats[0]), float(stats[1]), float(stats[2])
-            self.weight_ess.append(total * total / total2 if total2 > 0 else float("nan"))
+                                            else L.BK_F64, mode, stats.data_ptr(), wp, wn, st))
+            self._stats_log.append(stats)   # stays on device: no host sync per temperature
             if res_uniforms is not None:
                 ru = to_dev(res_uniforms, self.dtype, self.device).reshape(-1)
                 if mode == L.RESAMPLE_MULTINOMIAL and ru.numel() == Mg and self._world > 1:
@@ -141,10 +148,9 @@ class TemperedLikelihoodSMC:
                 ru = None
             idx = torch.empty(Ml, dtype=torch.int64, device=self.device)
             rrng = make_rng(self._seed, n, 0)
-            L.check(lib.bk_smc_resample_indices(
+            L.check(lib.bk_smc_resample_indices_dev(
                 logw_all.data_ptr(), Mg, L.BK_F32 if self.dtype == torch.float32 else L.BK_F64, mode,
-                shift, total if mode == L.RESAMPLE_MULTINOMIAL else 1.0, ptr(ru), C.byref(rrng), Ml,
-                self._lo, idx.data_ptr(), None, wp, wn, st))
+                stats.data_ptr(), ptr(ru), C.byref(rrng), Ml, self._lo, idx.data_ptr(), None, wp, wn, st))
             new = torch.empty_like(self.thetas)
             L.check(lib.bk_gather_rows(thetas_all.data_ptr(), idx.data_ptr(), Ml, self.D,
                                        L.BK_F32 if self.dtype == torch.float32 else L.BK_F64,

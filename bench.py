@@ -230,6 +230,8 @@ def main():
     lib.bk_profile_enable(0)
     gms, gn = _lib.f64(0), _lib.u64(0)
     lib.bk_profile_read(_lib.PROF_GRAD, gms, gn)
+    sms_, sn = _lib.f64(0), _lib.u64(0)
+    lib.bk_profile_read(_lib.PROF_STEP, sms_, sn)
     accept = float(sampler.last_accept.float().mean())
     clk = clocks.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -272,22 +274,36 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (the gradient GEMM) ----------------------------
+    # ---- roofline of the dominant kernel -----------------------------------------------
+    # k_dense_tc in STEP mode (gradient GEMM + fused leapfrog update): L-1 of the L
+    # gradient launches of a step and ~3/4 of its time.  It is HBM-bound: SURVEY 8(d)
+    # c2 "HBM side" = 4*D*s bytes per chain per leapfrog step (theta, rho round trip).
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0   # fallback: B200_PROFILING.md sustained figure
-    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback"
-    flops_per_launch = 2.0 * C * D * D                       # 2*C*D^2 per gradient
+    peak_bw = peaks.get("hbm_gbs") or 6650.0               # fallback: B200_PROFILING.md
+    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    bytes_per_launch = 4.0 * D * 4 * C                      # 16 KB per chain-leapfrog-step
+    s_avg_ms = sms_.value / max(sn.value, 1)
     g_avg_ms = gms.value / max(gn.value, 1)
-    achieved = flops_per_launch / (g_avg_ms * 1e-3) / 1e12 if gn.value else None
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
-                "kernel": "dense-precision gradient GEMM", "launches_timed": int(gn.value),
-                "avg_launch_ms": g_avg_ms, "share_of_step": gms.value / ms if ms else None,
-                "peak_source": peak_src}
+    achieved = bytes_per_launch / (s_avg_ms * 1e-3) / 1e9 if sn.value else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_bw, "unit": "GB/s",
+                "frac": (achieved / peak_bw) if achieved else None,
+                # ncu --set full, profiles/: dram read+write per STEP launch (incl. the bf16 operand copy)
+                "traffic": 1.31e9 if C == CHAINS_PER_GPU else None,
+                "kernel": "k_dense_tc STEP mode (tcgen05 gradient GEMM + fused leapfrog epilogue)",
+                "launches_timed": int(sn.value), "avg_launch_ms": s_avg_ms,
+                "share_of_step": sms_.value / ms if ms else None, "peak_source": peak_src,
+                "tensor_side": {  # the endpoint gradient (3-pass bf16 split) is tensor-bound
+                    "kernel": "k_dense_tc GRAD mode", "flops_per_launch": 3 * 2.0 * C * D * D,
+                    "avg_launch_ms": g_avg_ms, "launches_timed": int(gn.value),
+                    "achieved_tflops": (3 * 2.0 * C * D * D / (g_avg_ms * 1e-3) / 1e12) if gn.value else None,
+                    "peak_tflops": peak_tf,
+                    "frac": (3 * 2.0 * C * D * D / (g_avg_ms * 1e-3) / 1e12 / peak_tf) if gn.value else None,
+                    "share_of_step": gms.value / ms if ms else None}}
 
     cpu = None if args.no_cpu_baseline else cpu_baseline_single()
     line = {

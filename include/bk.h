@@ -103,8 +103,9 @@ BK_API uint64_t bk_launch_count(void);
  * the launch stream (bench.py's live roofline measurement).  bk_profile_read
  * synchronises the recorded events, returns the summed device time and launch
  * count of `tag` since the last read, and resets that tag. */
-enum { BK_PROF_GRAD = 0,      /* model gradient kernel (GEMM for the dense plugin) */
-       BK_PROF_SAMPLER = 1,   /* fused sampler kernel                              */
+enum { BK_PROF_GRAD = 0,      /* model gradient kernel (dense plugin: GEMM, tcgen05 GRAD mode) */
+       BK_PROF_SAMPLER = 1,   /* fused sampler kernel                                          */
+       BK_PROF_STEP = 2,      /* tcgen05 GEMM with the fused leapfrog epilogue (STEP mode)     */
        BK_PROF_NTAGS = 4 };
 BK_API int bk_profile_enable(int32_t on);
 BK_API int bk_profile_read(int32_t tag, double* total_ms_out, uint64_t* launches_out);
@@ -194,6 +195,12 @@ BK_API int bk_smc_weight_stats(const void* logw, int64_t M, int32_t dtype, int32
  * slice).  idx_out [n_points] int64; cdf_out [M] f64 or NULL (scratch in ws). */
 BK_API int bk_smc_resample_indices(const void* logw, int64_t M, int32_t dtype, int32_t mode,
                             double shift, double total, const void* uniforms, const bk_rng* rng,
+                            int64_t n_points, int64_t point_offset, int64_t* idx_out,
+                            void* cdf_out, void* ws, size_t ws_bytes, void* stream);
+/* Same, with the normaliser read ON DEVICE from `stats` (the 3 doubles
+ * bk_smc_weight_stats wrote): no host round trip between the two calls. */
+BK_API int bk_smc_resample_indices_dev(const void* logw, int64_t M, int32_t dtype, int32_t mode,
+                            const double* stats, const void* uniforms, const bk_rng* rng,
                             int64_t n_points, int64_t point_offset, int64_t* idx_out,
                             void* cdf_out, void* ws, size_t ws_bytes, void* stream);
 /* thetas[idxs] (smc.py:75): out [M,D] = src[idx] */
