@@ -36,7 +36,43 @@ __global__ void __launch_bounds__(128) k_sep_sampler(SepArgs<T> a) {
         const T logu = log_u(ln.uniform(a.rng, a.C, chain, t, 0));
         bool acc;
         T out_lp;
-        if constexpr (ALGO == ALGO_HMC) {
+        if constexpr (ALGO == ALGO_HMC && MK == MK_ISO && sizeof(T) == 4) {
+            // fp32 timed mode, isotropic target: same leapfrog (hmc.py:40-63) with the
+            // constants folded (kick = one FMA) and log p - kinetic reduced in ONE
+            // group shuffle per Hamiltonian: the kernel is issue-bound, not HBM-bound.
+            const T prec = md.prec_scalar;
+            const T kick = -a.eps * prec, hkick = -a.half_eps * prec;
+            T s0 = T(0);
+#pragma unroll
+            for (int k = 0; k < NE; ++k) s0 = fmaf(prec * th[k], th[k], fmaf(z[k], z[k], s0));
+            const T h0 = T(-0.5) * group_sum<G>(s0);
+            T q[NE];
+#pragma unroll
+            for (int k = 0; k < NE; ++k) {
+                q[k] = th[k];
+                z[k] = fmaf(-hkick, th[k], z[k]);   // backward half kick (hmc.py:46)
+            }
+            for (int s = 0; s < a.L; ++s) {
+#pragma unroll
+                for (int k = 0; k < NE; ++k) {
+                    z[k] = fmaf(kick, q[k], z[k]);
+                    q[k] = fmaf(a.eps, z[k], q[k]);
+                }
+            }
+            T s1 = T(0);
+#pragma unroll
+            for (int k = 0; k < NE; ++k) {
+                z[k] = fmaf(hkick, q[k], z[k]);     // forward half kick (hmc.py:52)
+                s1 = fmaf(prec * q[k], q[k], fmaf(z[k], z[k], s1));
+            }
+            const T h1 = T(-0.5) * group_sum<G>(s1);
+            acc = logu < h1 - h0;
+            if (acc) {
+#pragma unroll
+                for (int k = 0; k < NE; ++k) th[k] = q[k];
+            }
+            out_lp = acc ? h1 : h0;
+        } else if constexpr (ALGO == ALGO_HMC) {
             // hmc.py:55-63
             const T h0 = A::sub(md.logp(th), md.kinetic(z));
             T q[NE];

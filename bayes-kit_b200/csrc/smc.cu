@@ -138,14 +138,28 @@ __global__ void k_max_partial(const T* __restrict__ x, int64_t n, double* __rest
     }
 }
 
-// stats[0] = max (or 0 when !shift), then sums of exp(x - stats[0]) and its square
-template <typename T>
-__global__ void k_sum_partial(const T* __restrict__ x, int64_t n, const double* __restrict__ maxpart,
-                              int nmax, int use_shift, double* __restrict__ part) {
+// single block: out[0] = max over the block partials (0 when the weights are not shifted)
+__global__ void k_max_final(const double* __restrict__ maxpart, int nb, int use_shift, double* __restrict__ out) {
     __shared__ double sm[33];
-    double mx = -INFINITY;
-    for (int i = 0; i < nmax; ++i) mx = fmax(mx, maxpart[i]);
-    const double shift = use_shift ? mx : 0.0;
+    double v = -INFINITY;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) v = fmax(v, maxpart[i]);
+    v = warp_max(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = lane < (blockDim.x >> 5) ? sm[lane] : -INFINITY;
+        v = warp_max(v);
+        if (lane == 0) out[0] = use_shift ? v : 0.0;
+    }
+}
+
+// per-block sums of exp(x - shift) and its square, shift = stats[0]
+template <typename T>
+__global__ void k_sum_partial(const T* __restrict__ x, int64_t n, const double* __restrict__ stats,
+                              double* __restrict__ part) {
+    __shared__ double sm[33];
+    const double shift = stats[0];
     double s = 0, s2 = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double w = exp((double)x[i] - shift);
@@ -160,16 +174,17 @@ __global__ void k_sum_partial(const T* __restrict__ x, int64_t n, const double* 
     }
 }
 
-__global__ void k_stats_final(const double* __restrict__ maxpart, const double* __restrict__ part,
-                              int nb, int use_shift, double* __restrict__ out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double mx = -INFINITY, s = 0, s2 = 0;
-        for (int i = 0; i < nb; ++i) {
-            mx = fmax(mx, maxpart[i]);
-            s += part[2 * i];
-            s2 += part[2 * i + 1];
-        }
-        out[0] = use_shift ? mx : 0.0;
+// single block, fixed order: out[1] = sum w, out[2] = sum w^2
+__global__ void k_stats_final(const double* __restrict__ part, int nb, double* __restrict__ out) {
+    __shared__ double sm[33];
+    double s = 0, s2 = 0;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        s += part[2 * i];
+        s2 += part[2 * i + 1];
+    }
+    s = block_sum(s, sm);
+    s2 = block_sum(s2, sm);
+    if (threadIdx.x == 0) {
         out[1] = s;
         out[2] = s2;
     }
@@ -220,17 +235,34 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_local(const T* __restrict
     if (threadIdx.x == SCAN_THREADS - 1) block_tot[blockIdx.x] = excl + run;
 }
 
-// exclusive scan of the block totals (single block, sequential over chunks)
-__global__ void k_scan_blocks(double* __restrict__ block_tot, int nb, double* __restrict__ grand) {
-    if (threadIdx.x == 0) {
-        double run = 0;
-        for (int i = 0; i < nb; ++i) {
-            double t = block_tot[i];
-            block_tot[i] = run;
-            run += t;
+// exclusive scan of the block totals: one CTA of 1024 threads walks chunks of 1024 totals
+__global__ void __launch_bounds__(1024) k_scan_blocks(double* __restrict__ block_tot, int nb,
+                                                      double* __restrict__ grand) {
+    __shared__ double wsum[32];
+    __shared__ double carry_s;
+    if (threadIdx.x == 0) carry_s = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = 0; base < nb; base += 1024) {
+        const int i = base + threadIdx.x;
+        const double v = i < nb ? block_tot[i] : 0.0;
+        double inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
         }
-        *grand = run;
+        if (lane == 31) wsum[w] = inc;
+        __syncthreads();
+        double woff = 0;
+        for (int k = 0; k < w; ++k) woff += wsum[k];
+        const double carry = carry_s;
+        if (i < nb) block_tot[i] = carry + woff + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + woff + inc;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) *grand = carry_s;
 }
 
 __global__ void k_scan_finish(double* __restrict__ cdf, int64_t n, const double* __restrict__ block_off,
@@ -323,17 +355,15 @@ int bk_smc_weight_stats(const void* logw, int64_t M, int32_t dtype, int32_t mode
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = stat_blocks(M);
     const int shift = mode == BK_RESAMPLE_SYSTEMATIC;
-    if (dtype == BK_F64) {
-        k_max_partial<double><<<nb, RED_THREADS, 0, st>>>((const double*)logw, M, maxp);
-        BK_LAUNCH_CHECK();
-        k_sum_partial<double><<<nb, RED_THREADS, 0, st>>>((const double*)logw, M, maxp, nb, shift, sump);
-    } else {
-        k_max_partial<float><<<nb, RED_THREADS, 0, st>>>((const float*)logw, M, maxp);
-        BK_LAUNCH_CHECK();
-        k_sum_partial<float><<<nb, RED_THREADS, 0, st>>>((const float*)logw, M, maxp, nb, shift, sump);
-    }
+    if (dtype == BK_F64) k_max_partial<double><<<nb, RED_THREADS, 0, st>>>((const double*)logw, M, maxp);
+    else k_max_partial<float><<<nb, RED_THREADS, 0, st>>>((const float*)logw, M, maxp);
     BK_LAUNCH_CHECK();
-    k_stats_final<<<1, 32, 0, st>>>(maxp, sump, nb, shift, stats_out);
+    k_max_final<<<1, 256, 0, st>>>(maxp, nb, shift, stats_out);
+    BK_LAUNCH_CHECK();
+    if (dtype == BK_F64) k_sum_partial<double><<<nb, RED_THREADS, 0, st>>>((const double*)logw, M, stats_out, sump);
+    else k_sum_partial<float><<<nb, RED_THREADS, 0, st>>>((const float*)logw, M, stats_out, sump);
+    BK_LAUNCH_CHECK();
+    k_stats_final<<<1, 256, 0, st>>>(sump, nb, stats_out);
     BK_LAUNCH_CHECK();
     return BK_OK;
 }
@@ -365,7 +395,7 @@ static int resample_impl(const void* logw, int64_t M, int32_t dtype, int32_t mod
         k_scan_local<float><<<nb, SCAN_THREADS, 0, st>>>((const float*)logw, M, shift, total, stats, mode, cdf,
                                                           btot);
     BK_LAUNCH_CHECK();
-    k_scan_blocks<<<1, 32, 0, st>>>(btot, nb, btot + nb);
+    k_scan_blocks<<<1, 1024, 0, st>>>(btot, nb, btot + nb);
     BK_LAUNCH_CHECK();
     k_scan_finish<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(cdf, M, btot, btot + nb);
     BK_LAUNCH_CHECK();

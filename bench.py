@@ -274,6 +274,19 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- min-ESS/s (BASELINE metric): ESS per chain-step from a side run of the same
+    # sampler on 2048 chains x 200 draws (device diagnostics, Geyer IMSE like ess.py:52-69),
+    # scaled by the measured chain-steps/s.  Anti-correlated chains give ESS > n (or an
+    # IAT <= 0): those are counted as n draws (conservative).
+    n_side, c_side = 200, 2048
+    side = bk.HMCDiag(model, EPS, L, chains=c_side, seed=1)
+    side.sample_n(50, keep_draws=False)
+    dr, _ = side.sample_n(n_side)
+    e = bk.ess(dr, draws_first=True)                     # [chains, params]
+    e = torch.where((e <= 0) | (e > n_side), torch.full_like(e, float(n_side)), e)
+    ess_per_step = float(e.mean(0).min()) / n_side       # min over parameters
+    del dr, e, side
+
     # ---- roofline of the dominant kernel -----------------------------------------------
     # k_dense_tc in STEP mode (gradient GEMM + fused leapfrog update): L-1 of the L
     # gradient launches of a step and ~3/4 of its time.  It is HBM-bound: SURVEY 8(d)
@@ -313,7 +326,8 @@ def main():
         "config": {"workload": f"c2: HMCDiag L={L} eps={EPS}, {C} chains/GPU x {D}-dim dense-precision "
                                f"Gaussian (P=AA^T/D+I, seed 0), device Philox",
                    "chains_per_gpu": C, "dims": D, "leapfrog_steps": L, "accept_rate": accept,
-                   "grad_evals_per_s": value * L,
+                   "grad_evals_per_s": value * L, "min_ess_per_s": value * ess_per_step,
+                   "ess_per_chain_step_min_param": ess_per_step,
                    "l2": "inputs larger than L2 (>= 1.5 GB of chain state streamed per step)"},
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": C * D * 4,
