@@ -18,10 +18,13 @@
 // with a 3-pass bf16 split (P_hi*q_hi + P_hi*q_lo + P_lo*q_hi, ~2^-16
 // relative) so the Metropolis test sees fp32-accurate energies.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator +
-// single-thread MMA issuer, warps 2..5 = epilogue (TMEM lane quarter = warp%4).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator +
+// single-thread MMA issuer, warps 2..9 = epilogue (TMEM lane quarter = warp%4,
+// column half = (warp-2)/4), two 16-chain chunks of r/q loads in flight per warp.
+// Work arrays are tile-/box-blocked so each CTA streams contiguous runs.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "dense_tc.h"
 #include "sep_common.cuh"
@@ -147,6 +150,18 @@ __host__ __device__ __forceinline__ int64_t box_index(int64_t row, int k, int kb
     return (((row / RB) * kblocks + (k / BK)) * RB + (row % RB)) * (int64_t)BK + (k % BK);
 }
 
+// asynchronous variant: the registers are valid only after tmem_wait_ld()
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+          "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 struct StepArgs {
     int mode;          // TC_MODE_STEP | TC_MODE_GRAD
     int n_pass;        // 1 (bf16) or 3 (bf16x3 split)
@@ -164,6 +179,7 @@ struct StepArgs {
     __nv_bfloat16* q_lo_next;  // [C, Dp] or NULL
     float* g_out;         // [C, D] row-major, or tile-blocked when g_blocked
     int g_blocked;
+    int debug;            // BK_TC_DEBUG bits: 1 = skip TMA+MMA, 2 = skip epilogue global traffic
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -205,7 +221,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (lane == 0 && !(a.debug & 1)) {
             int stage = 0;
             uint32_t phase = 0;
             for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -227,7 +243,15 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one thread) =================
-        if (lane == 0) {
+        if (lane == 0 && (a.debug & 1)) {   // experiment: no GEMM, just hand the accumulators over
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(tempty(acc), acc_phase ^ 1u);
+                mbar_arrive(tfull(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        } else if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -292,6 +316,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                 // chunks of CW chains; two chunks of r/q loads stay in flight ahead of the math
                 constexpr int CW = 16, NC = NCH * 32 / CW;
                 const bool full_tile = d_ok && cbase + NCH * 32 <= a.C;   // no per-element bounds
+                const bool no_mem = (a.debug & 2) != 0;
                 const int64_t e0 = blk_index(cbase, d, a.m_tiles);
                 const float* rp = a.r + e0;
                 const float* qp = a.q + e0;
@@ -304,7 +329,10 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                 const float eps = a.eps;
                 auto load = [&](int ch, float (&rb)[CW], float (&qb)[CW]) {
                     const int64_t o = (int64_t)ch * CW * D;
-                    if (full_tile) {
+                    if (no_mem) {
+#pragma unroll
+                        for (int j = 0; j < CW; ++j) { rb[j] = 0.f; qb[j] = 0.f; }
+                    } else if (full_tile) {
 #pragma unroll
                         for (int j = 0; j < CW; ++j) {
                             rb[j] = __ldcs(rp + o + (int64_t)j * D);
@@ -325,7 +353,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                     const int64_t o = (int64_t)ch * CW * D, ob = (int64_t)ch * CW * Dp;
 #pragma unroll
                     for (int j = 0; j < CW; ++j) {
-                        if (full_tile || (d_ok && cbase + ch * CW + j < a.C)) {
+                        if (!no_mem && (full_tile || (d_ok && cbase + ch * CW + j < a.C))) {
                             const float g = cv - __uint_as_float(v[j]);
                             const float rn = fmaf(em, g, rb[j]);    // r += eps * m * g
                             const float qn = fmaf(eps, rn, qb[j]);  // q += eps * r
@@ -742,6 +770,7 @@ int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* 
     a.m_tiles = (int)(m.Dp / tc::BM); a.n_tiles = (C + tc::BN - 1) / tc::BN; a.kblocks = (int)(m.Dp / tc::BK);
     a.eps = (float)eps; a.metric = metric; a.cvec = (const float*)m.Pmu; a.r = r; a.q = q; a.g_out = gq;
     a.g_blocked = 1;
+    { const char* e = getenv("BK_TC_DEBUG"); a.debug = e ? atoi(e) : 0; }
     const unsigned wblocks = (unsigned)((C * 32 + 255) / 256);
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     const bool vec = D % 4 == 0 && al16(theta) && al16(grad) && al16(metric) && al16(m.d.mu) &&
