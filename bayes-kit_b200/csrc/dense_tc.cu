@@ -37,12 +37,24 @@ constexpr int BM = 128;      // dims per tile  (UMMA M, TMEM lanes)
 constexpr int BN = 256;      // chains per tile (UMMA N, TMEM columns)
 constexpr int BK = 64;       // k per stage (128 bytes of bf16 = one swizzle atom row)
 constexpr int UK = 16;       // UMMA K for bf16
-constexpr int STAGES = 4;
-constexpr int A_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_BYTES = BN * BK * 2;   // 32 KB
-constexpr int SMEM_TILES = STAGES * (A_BYTES + B_BYTES);
-constexpr int SMEM_BYTES = SMEM_TILES + 256 + 1024;  // + barriers + 1024B alignment slack
-constexpr int EPI_WARPS = 8;            // 2 per TMEM lane quarter (column halves)
+// GRAD mode is tensor-bound: 4 operand stages.  STEP mode is HBM-bound on its epilogue:
+// 2 operand stages, and the freed 128 KB is a per-warp cp.async ring that keeps
+// EDEPTH-1 chunks (16 chains x 32 dims of r and q = 4 KB) per epilogue warp in flight.
+constexpr int CWID = 16;                               // chains per epilogue chunk
+constexpr int EDEPTH = 4;                              // ring depth per epilogue warp
+constexpr int ECHUNK_BYTES = 2 * CWID * 32 * 4;        // r + q of one chunk of one warp
+template <int MODE> struct Cfg {
+    // STEP stages are HALF k-blocks (32 k = 64-byte rows, SWIZZLE_64B): 4 x 24 KB keeps the same
+    // 96 KB of operands in flight as 2 x 48 KB but with twice the pipeline granularity.
+    static constexpr int KS = MODE == TC_MODE_STEP ? 32 : 64;          // k per stage
+    static constexpr int STAGES = 4;
+    static constexpr int A_BYTES = BM * KS * 2;
+    static constexpr int B_BYTES = BN * KS * 2;
+    static constexpr int SMEM_TILES = STAGES * (A_BYTES + B_BYTES);
+    static constexpr int ERING = MODE == TC_MODE_STEP ? 8 * EDEPTH * ECHUNK_BYTES : 0;
+    static constexpr int SMEM_BYTES = SMEM_TILES + ERING + 256 + 1024;  // + barriers + alignment slack
+};
+constexpr int EPI_WARPS = 8;            // 2 per TMEM lane quarter (column halves); ring sized for 8
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -81,14 +93,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart
+// K-major swizzled operand tile: rows of ROWB bytes (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B),
+// 8-row groups 8*ROWB bytes apart
+template <int ROWB>
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address, bits [0,14)
-    d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024u >> 4) << 32;           // stride byte offset = 1024 B, bits [32,46)
-    d |= (uint64_t)1 << 46;                      // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                      // layout type: SWIZZLE_128B
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);            // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                               // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)((8u * ROWB) >> 4) << 32;              // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                               // descriptor version (sm_100)
+    d |= (uint64_t)(ROWB == 128 ? 2 : 4) << 61;           // layout type: SWIZZLE_128B = 2, SWIZZLE_64B = 4
     return d;
 }
 // kind::f16, A = B = bf16, D = f32, both K-major, M = 128, N = 256
@@ -182,6 +196,14 @@ struct StepArgs {
     int debug;            // BK_TC_DEBUG bits: 1 = skip TMA+MMA, 2 = skip epilogue global traffic
 };
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
            const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
@@ -189,8 +211,13 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B swizzle atoms
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr int STAGES = Cfg<MODE>::STAGES;
+    constexpr int SMEM_TILES = Cfg<MODE>::SMEM_TILES;
+    constexpr int KS = Cfg<MODE>::KS, A_BYTES = Cfg<MODE>::A_BYTES, B_BYTES = Cfg<MODE>::B_BYTES;
+    constexpr int SPK = BK / KS;                               // stages per 64-wide k-block
     const uint32_t sA = base, sB = base + STAGES * A_BYTES;
-    const uint32_t bars = base + SMEM_TILES;
+    const uint32_t ering = base + SMEM_TILES;                 // STEP: per-warp r/q rings
+    const uint32_t bars = ering + Cfg<MODE>::ERING;
     auto full = [&](int s) { return bars + 8u * s; };
     auto empty = [&](int s) { return bars + 8u * (STAGES + s); };
     auto tfull = [&](int s) { return bars + 8u * (2 * STAGES + s); };
@@ -217,7 +244,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     const int64_t total_tiles = a.n_tiles * a.m_tiles;
-    const int iters = a.n_pass * a.kblocks;
+    const int iters = a.n_pass * a.kblocks * SPK;
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -228,14 +255,15 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                 const int m_tile = (int)(tile % a.m_tiles);
                 const int64_t n_tile = tile / a.m_tiles;
                 for (int it = 0; it < iters; ++it) {
-                    const int pass = it / a.kblocks, kb = it % a.kblocks;
+                    const int pass = it / (a.kblocks * SPK), ks = it % (a.kblocks * SPK);
+                    const int kb = ks / SPK, kx = (ks % SPK) * KS;   // 64-wide box, k offset inside it
                     // pass 0: (A_hi, B_hi)  pass 1: (A_hi, B_lo)  pass 2: (A_lo, B_hi)
                     const CUtensorMap* ma = pass == 2 ? &mapA1 : &mapA0;
                     const CUtensorMap* mb = pass == 1 ? &mapB1 : &mapB0;
                     mbar_wait(empty(stage), phase ^ 1u);
                     mbar_expect_tx(full(stage), A_BYTES + B_BYTES);
-                    tma_load_2d(sA + stage * A_BYTES, ma, full(stage), 0, (m_tile * a.kblocks + kb) * BM);
-                    tma_load_2d(sB + stage * B_BYTES, mb, full(stage), 0,
+                    tma_load_2d(sA + stage * A_BYTES, ma, full(stage), kx, (m_tile * a.kblocks + kb) * BM);
+                    tma_load_2d(sB + stage * B_BYTES, mb, full(stage), kx,
                                 (int)((n_tile * a.kblocks + kb) * BN));
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -265,8 +293,8 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                     tc_fence_after();
                     const uint32_t a0 = sA + stage * A_BYTES, b0 = sB + stage * B_BYTES;
 #pragma unroll
-                    for (int k = 0; k < BK / UK; ++k)
-                        umma(d_tmem, umma_desc(a0 + k * UK * 2), umma_desc(b0 + k * UK * 2),
+                    for (int k = 0; k < KS / UK; ++k)
+                        umma(d_tmem, umma_desc<KS * 2>(a0 + k * UK * 2), umma_desc<KS * 2>(b0 + k * UK * 2),
                              (it | k) != 0 ? 1u : 0u);
                     umma_commit(empty(stage));            // smem slot reusable once these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -277,26 +305,22 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         }
     } else {
         // ================= epilogue: 8 warps, lane = dim, registers = chains =================
-        // warp -> TMEM lane quarter (warp % 4) and column half; each warp walks its 4
-        // chunks of 32 chains with the NEXT chunk's r/q loads already in flight
-        // (issued before the accumulator is even ready), so ~64 KB per SM stay
-        // outstanding and the HBM latency is covered.
+        // warp -> TMEM lane quarter (warp % 4) and column half (128 chains).
         const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;                  // column slice of this warp
+        const int half = (warp - 2) >> 2;
         constexpr int NCH = BN / 32 / (EPI_WARPS / 4);     // 32-chain groups per warp
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_tile = (int)(tile % a.m_tiles);
-            const int64_t n_tile = tile / a.m_tiles;
-            const int d = m_tile * BM + quarter * 32 + lane;
-            const bool d_ok = d < a.D;
-            const float cv = (a.cvec && d_ok) ? a.cvec[d] : 0.0f;
-            const float em = a.eps * ((a.metric && d_ok) ? a.metric[d] : 1.0f);
-            const uint32_t t0 = tmem_base + (uint32_t)acc * BN + ((uint32_t)(quarter * 32) << 16) +
-                                (uint32_t)(half * NCH * 32);
-            const int64_t cbase = n_tile * BN + half * NCH * 32;
-            if (a.mode == TC_MODE_GRAD) {
+        if constexpr (MODE == TC_MODE_GRAD) {
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_tile = (int)(tile % a.m_tiles);
+                const int64_t n_tile = tile / a.m_tiles;
+                const int d = m_tile * BM + quarter * 32 + lane;
+                const bool d_ok = d < a.D;
+                const float cv = (a.cvec && d_ok) ? a.cvec[d] : 0.0f;
+                const uint32_t t0 = tmem_base + (uint32_t)acc * BN + ((uint32_t)(quarter * 32) << 16) +
+                                    (uint32_t)(half * NCH * 32);
+                const int64_t cbase = n_tile * BN + half * NCH * 32;
                 mbar_wait(tfull(acc), acc_phase);
                 tc_fence_after();
 #pragma unroll 1
@@ -312,81 +336,99 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                                 cv - __uint_as_float(v[j]);
                     }
                 }
-            } else {
-                // chunks of CW chains; two chunks of r/q loads stay in flight ahead of the math
-                constexpr int CW = 16, NC = NCH * 32 / CW;
-                const bool full_tile = d_ok && cbase + NCH * 32 <= a.C;   // no per-element bounds
-                const bool no_mem = (a.debug & 2) != 0;
+                tc_fence_before();
+                mbar_arrive(tempty(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        } else {
+            // STEP: fused leapfrog update.  Each warp streams ITS 16-chain x 32-dim pieces of
+            // r and q through a private cp.async ring in shared memory (EDEPTH-1 chunks =
+            // 12 KB per warp, 96 KB per SM in flight, no registers held, prefetch runs
+            // across tile boundaries and ahead of the accumulator), then updates from
+            // registers:  r += eps*m*g ; q += eps*r ; q_hi(next operand) = bf16(q).
+            constexpr int NC = NCH * 32 / CWID;                 // chunks per warp per tile
+            const bool no_mem = (a.debug & 2) != 0;
+            const uint32_t ring = ering + (uint32_t)(warp - 2) * (EDEPTH * ECHUNK_BYTES);
+            const int64_t n_my = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+            const int64_t total_chunks = n_my * NC;
+            const int row_in = lane >> 3, seg = lane & 7;       // cp.async: 4 rows x 8 x 16 B per instruction
+            auto chunk_elem0 = [&](int64_t g) -> int64_t {      // element offset of (chain row 0, dim 0) of chunk g
+                const int64_t tile = blockIdx.x + (g / NC) * gridDim.x;
+                const int ch = (int)(g % NC);
+                const int m_tile = (int)(tile % a.m_tiles);
+                const int64_t n_tile = tile / a.m_tiles;
+                return blk_index(n_tile * BN + half * NCH * 32 + ch * CWID, m_tile * BM + quarter * 32, a.m_tiles);
+            };
+            auto issue = [&](int64_t g) {
+                if (g < total_chunks && !no_mem) {
+                    const int64_t e0 = chunk_elem0(g);
+                    const uint32_t dst = ring + (uint32_t)(g % EDEPTH) * ECHUNK_BYTES;
+#pragma unroll
+                    for (int it = 0; it < CWID / 4; ++it) {
+                        const int row = it * 4 + row_in;
+                        const int64_t eo = e0 + (int64_t)row * BM + seg * 4;
+                        const uint32_t so = (uint32_t)(row * 128 + seg * 16);
+                        cp_async16(dst + so, a.r + eo);
+                        cp_async16(dst + CWID * 128 + so, a.q + eo);
+                    }
+                }
+                cp_async_commit();
+            };
+#pragma unroll
+            for (int p = 0; p < EDEPTH - 1; ++p) issue(p);
+            int64_t g = 0;
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_tile = (int)(tile % a.m_tiles);
+                const int64_t n_tile = tile / a.m_tiles;
+                const int d = m_tile * BM + quarter * 32 + lane;
+                const bool d_ok = d < a.D;
+                const float cv = (a.cvec && d_ok) ? a.cvec[d] : 0.0f;
+                const float em = a.eps * ((a.metric && d_ok) ? a.metric[d] : 1.0f);
+                const float eps = a.eps;
+                const uint32_t t0 = tmem_base + (uint32_t)acc * BN + ((uint32_t)(quarter * 32) << 16) +
+                                    (uint32_t)(half * NCH * 32);
+                const int64_t cbase = n_tile * BN + half * NCH * 32;
+                const bool full_tile = d_ok && cbase + NCH * 32 <= a.C;
                 const int64_t e0 = blk_index(cbase, d, a.m_tiles);
-                const float* rp = a.r + e0;
-                const float* qp = a.q + e0;
                 float* rw = a.r + e0;
                 float* qw = a.q + e0;
-                const int64_t b0i = box_index(cbase, d, a.kblocks, BN);   // chain stride inside a box = BK
+                const int64_t b0i = box_index(cbase, d, a.kblocks, BN);
                 __nv_bfloat16* hw = a.q_hi_next + b0i;
                 __nv_bfloat16* lw = a.q_lo_next ? a.q_lo_next + b0i : nullptr;
-                const int D = BM, Dp = BK;     // chain strides inside the blocked fp32 tile / bf16 box
-                const float eps = a.eps;
-                auto load = [&](int ch, float (&rb)[CW], float (&qb)[CW]) {
-                    const int64_t o = (int64_t)ch * CW * D;
-                    if (no_mem) {
-#pragma unroll
-                        for (int j = 0; j < CW; ++j) { rb[j] = 0.f; qb[j] = 0.f; }
-                    } else if (full_tile) {
-#pragma unroll
-                        for (int j = 0; j < CW; ++j) {
-                            rb[j] = __ldcs(rp + o + (int64_t)j * D);
-                            qb[j] = __ldcs(qp + o + (int64_t)j * D);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < CW; ++j) {
-                            const bool ok = d_ok && cbase + ch * CW + j < a.C;
-                            rb[j] = ok ? rp[o + (int64_t)j * D] : 0.0f;
-                            qb[j] = ok ? qp[o + (int64_t)j * D] : 0.0f;
-                        }
-                    }
-                };
-                auto process = [&](int ch, const float (&rb)[CW], const float (&qb)[CW]) {
-                    uint32_t v[CW];
-                    tmem_ld16(t0 + ch * CW, v);
-                    const int64_t o = (int64_t)ch * CW * D, ob = (int64_t)ch * CW * Dp;
-#pragma unroll
-                    for (int j = 0; j < CW; ++j) {
-                        if (!no_mem && (full_tile || (d_ok && cbase + ch * CW + j < a.C))) {
-                            const float g = cv - __uint_as_float(v[j]);
-                            const float rn = fmaf(em, g, rb[j]);    // r += eps * m * g
-                            const float qn = fmaf(eps, rn, qb[j]);  // q += eps * r
-                            __stcs(rw + o + (int64_t)j * D, rn);
-                            __stcs(qw + o + (int64_t)j * D, qn);
-                            const __nv_bfloat16 hi = __float2bfloat16_rn(qn);
-                            hw[ob + (int64_t)j * Dp] = hi;
-                            if (lw) lw[ob + (int64_t)j * Dp] = __float2bfloat16_rn(qn - __bfloat162float(hi));
-                        }
-                    }
-                };
-                float r0[CW], q0[CW], r1[CW], q1[CW], r2[CW], q2[CW];
-                load(0, r0, q0);
-                load(1, r1, q1);
                 mbar_wait(tfull(acc), acc_phase);
                 tc_fence_after();
 #pragma unroll 1
-                for (int ch = 0; ch < NC; ch += 3) {
-                    if (ch + 2 < NC) load(ch + 2, r2, q2);
-                    process(ch, r0, q0);
-                    if (ch + 1 < NC) {
-                        if (ch + 3 < NC) load(ch + 3, r0, q0);
-                        process(ch + 1, r1, q1);
+                for (int ch = 0; ch < NC; ++ch, ++g) {
+                    issue(g + EDEPTH - 1);
+                    cp_async_wait<EDEPTH - 1>();      // chunk g has landed
+                    __syncwarp();
+                    uint32_t v[CWID];
+                    tmem_ld16(t0 + ch * CWID, v);
+                    const uint32_t src = ring + (uint32_t)(g % EDEPTH) * ECHUNK_BYTES + (uint32_t)lane * 4;
+                    const int64_t o = (int64_t)ch * CWID * BM, ob = (int64_t)ch * CWID * BK;
+#pragma unroll
+                    for (int j = 0; j < CWID; ++j) {
+                        float rj, qj;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(rj) : "r"(src + j * 128));
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qj) : "r"(src + CWID * 128 + j * 128));
+                        if (!no_mem && (full_tile || (d_ok && cbase + ch * CWID + j < a.C))) {
+                            const float gj = cv - __uint_as_float(v[j]);
+                            const float rn = fmaf(em, gj, rj);    // r += eps * m * g
+                            const float qn = fmaf(eps, rn, qj);   // q += eps * r
+                            __stcs(rw + o + (int64_t)j * BM, rn);
+                            __stcs(qw + o + (int64_t)j * BM, qn);
+                            const __nv_bfloat16 hi = __float2bfloat16_rn(qn);
+                            hw[ob + (int64_t)j * BK] = hi;
+                            if (lw) lw[ob + (int64_t)j * BK] = __float2bfloat16_rn(qn - __bfloat162float(hi));
+                        }
                     }
-                    if (ch + 2 < NC) {
-                        if (ch + 4 < NC) load(ch + 4, r1, q1);
-                        process(ch + 2, r2, q2);
-                    }
+                    __syncwarp();                     // stage may be refilled by the next issue
                 }
+                tc_fence_before();
+                mbar_arrive(tempty(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
-            tc_fence_before();
-            mbar_arrive(tempty(acc));
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            cp_async_wait<0>();
         }
     }
     tc_fence_before();
@@ -610,16 +652,17 @@ static EncodeFn get_encode() {
 
 // bf16 row-major [rows, Dp] (pitch Dp), box = [box_rows x 64 k], 128B swizzle
 // box-blocked bf16 operand: a [n_boxes * box_rows, 64] matrix with 128-byte rows
-static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int Dp, int box_rows) {
+static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int Dp, int box_rows, int box_k) {
     EncodeFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return BK_E_CUDA; }
     const int64_t row_tiles = (rows + box_rows - 1) / box_rows;
     cuuint64_t dims[2] = {(cuuint64_t)BK, (cuuint64_t)(row_tiles * (Dp / BK) * box_rows)};
     cuuint64_t strides[1] = {(cuuint64_t)BK * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
     cuuint32_t el[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, el,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     box_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return BK_E_CUDA; }
     return BK_OK;
@@ -629,7 +672,10 @@ static int launch_tc(const Model& m, const StepArgs& a, const __nv_bfloat16* b_h
                      cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        BK_CUDA(cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        BK_CUDA(cudaFuncSetAttribute(k_dense_tc<TC_MODE_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg<TC_MODE_STEP>::SMEM_BYTES));
+        BK_CUDA(cudaFuncSetAttribute(k_dense_tc<TC_MODE_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg<TC_MODE_GRAD>::SMEM_BYTES));
         attr = true;
     }
     static int sms = 0;
@@ -640,15 +686,19 @@ static int launch_tc(const Model& m, const StepArgs& a, const __nv_bfloat16* b_h
     }
     CUtensorMap mA0, mA1, mB0, mB1;
     int rc;
-    if ((rc = make_map(&mA0, m.P_hi, m.Dp, (int)m.Dp, BM))) return rc;
-    if ((rc = make_map(&mA1, m.P_lo, m.Dp, (int)m.Dp, BM))) return rc;
-    if ((rc = make_map(&mB0, b_hi, a.C, (int)m.Dp, BN))) return rc;
-    if ((rc = make_map(&mB1, b_lo ? b_lo : b_hi, a.C, (int)m.Dp, BN))) return rc;
+    const int bk = a.mode == TC_MODE_STEP ? Cfg<TC_MODE_STEP>::KS : Cfg<TC_MODE_GRAD>::KS;
+    if ((rc = make_map(&mA0, m.P_hi, m.Dp, (int)m.Dp, BM, bk))) return rc;
+    if ((rc = make_map(&mA1, m.P_lo, m.Dp, (int)m.Dp, BM, bk))) return rc;
+    if ((rc = make_map(&mB0, b_hi, a.C, (int)m.Dp, BN, bk))) return rc;
+    if ((rc = make_map(&mB1, b_lo ? b_lo : b_hi, a.C, (int)m.Dp, BN, bk))) return rc;
     const int64_t tiles = a.n_tiles * a.m_tiles;
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
     const int tag = a.mode == TC_MODE_STEP ? BK_PROF_STEP : BK_PROF_GRAD;
     prof_begin(tag, st);
-    k_dense_tc<<<grid, THREADS, SMEM_BYTES, st>>>(mA0, mA1, mB0, mB1, a);
+    if (a.mode == TC_MODE_STEP)
+        k_dense_tc<TC_MODE_STEP><<<grid, THREADS, Cfg<TC_MODE_STEP>::SMEM_BYTES, st>>>(mA0, mA1, mB0, mB1, a);
+    else
+        k_dense_tc<TC_MODE_GRAD><<<grid, THREADS, Cfg<TC_MODE_GRAD>::SMEM_BYTES, st>>>(mA0, mA1, mB0, mB1, a);
     prof_end(tag, st);
     BK_LAUNCH_CHECK();
     return BK_OK;
