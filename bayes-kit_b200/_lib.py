@@ -58,6 +58,7 @@ _SIGNATURES = {
     "bk_model_dims": (i64, [u64]),
     "bk_model_eval_workspace_bytes": (sz, [u64, i64]),
     "bk_model_log_density_gradient": (C.c_int, [u64, vp, i64, vp, vp, vp, sz, vp]),
+    "bk_model_log_density_gradient_fast": (C.c_int, [u64, vp, i64, vp, vp, vp, sz, vp]),
     "bk_model_log_prior_likelihood": (C.c_int, [u64, vp, i64, vp, vp, vp]),
     "bk_hmc_diag_workspace_bytes": (sz, [u64, i64]),
     "bk_hmc_diag_sample": (C.c_int, [u64, vp, vp, vp, C.POINTER(i32), i64, f64, i32, vp, i64,

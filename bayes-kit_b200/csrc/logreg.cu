@@ -32,7 +32,7 @@ __device__ __forceinline__ T sigmoid_(T z) {
     return T(0.5) * (T(1) + tanh(T(0.5) * z));
 }
 
-template <typename T>
+template <typename T, bool WITH_GRAD>
 __global__ void __launch_bounds__(256) k_hlr_partial(const T* __restrict__ X, const T* __restrict__ y,
                                                      const T* __restrict__ theta, int64_t C, int64_t N,
                                                      int Dx, int D, int64_t rows_per_split,
@@ -95,9 +95,10 @@ __global__ void __launch_bounds__(256) k_hlr_partial(const T* __restrict__ X, co
             for (int j = 0; j < 4; ++j) {
                 const T zz = z[i][j];
                 if (live) ll[j] += yn * zz - softplus_(zz);
-                Rs[n * HLR_CT + tx + 16 * j] = live ? yn - sigmoid_(zz) : T(0);
+                if (WITH_GRAD) Rs[n * HLR_CT + tx + 16 * j] = live ? yn - sigmoid_(zz) : T(0);
             }
         }
+        if (!WITH_GRAD) continue;   // log-density only: no second contraction
         __syncthreads();
         // G[c = ty + 16 i][j = tx + 16 jj] += sum_n R[n][c] X[n][j]
         for (int n = 0; n < HLR_NT; ++n) {
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(256) k_hlr_partial(const T* __restrict__ X, co
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int64_t c = c0 + ty + 16 * i;
-        if (c >= C) continue;
+        if (c >= C || !WITH_GRAD) continue;
 #pragma unroll
         for (int jj = 0; jj < HLR_MAXJ; ++jj) {
             const int j = tx + 16 * jj;
@@ -185,14 +186,30 @@ size_t hlr_eval_ws_bytes(const Model& m, int64_t C) {
     const size_t es = m.d.dtype == BK_F64 ? 8 : 4;
     const int Dx = (int)m.d.dims - 2;
     const int ns = hlr_splits(C, m.d.n_obs);
-    return align_up((size_t)ns * C * Dx * es, 256) + align_up((size_t)ns * C * es, 256) + 512;
+    size_t b = align_up((size_t)ns * C * Dx * es, 256) + align_up((size_t)ns * C * es, 256) + 512;
+    if (hlr_tc_enabled(m)) {
+        size_t t = hlr_tc_eval_ws_bytes(m, C);
+        if (t > b) b = t;
+    }
+    return b;
 }
 
 template <typename T>
 static int hlr_eval_t(const Model& m, const T* theta, int64_t C, T* lp, T* grad, void* ws, size_t ws_bytes,
-                      cudaStream_t st) {
+                      cudaStream_t st, bool precise) {
     const int D = (int)m.d.dims, Dx = D - 2;
     const int64_t N = m.d.n_obs;
+    if constexpr (sizeof(T) == 4) {
+        if (!precise && hlr_tc_enabled(m)) {   // interior leapfrog gradient: tcgen05, bf16 operands
+            float *pg, *pl;
+            int ns;
+            int rc = hlr_tc_partial(m, theta, C, ws, ws_bytes, &pg, &pl, &ns, st);
+            if (rc) return rc;
+            k_hlr_finish<float><<<(unsigned)((C * 32 + 255) / 256), 256, 0, st>>>(theta, pg, pl, C, Dx, D, ns, lp, grad);
+            BK_LAUNCH_CHECK();
+            return BK_OK;
+        }
+    }
     if (Dx > 16 * HLR_MAXJ) {
         set_error("HIER_LOGREG supports up to %d regressors (got %d)", 16 * HLR_MAXJ, Dx);
         return BK_E_UNSUPPORTED;
@@ -211,13 +228,17 @@ static int hlr_eval_t(const Model& m, const T* theta, int64_t C, T* lp, T* grad,
     static bool attr32 = false, attr64 = false;
     bool& attr = sizeof(T) == 8 ? attr64 : attr32;
     if (!attr) {
-        BK_CUDA(cudaFuncSetAttribute(k_hlr_partial<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        BK_CUDA(cudaFuncSetAttribute(k_hlr_partial<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        BK_CUDA(cudaFuncSetAttribute(k_hlr_partial<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
     }
     if (smem > 200 * 1024) { set_error("HIER_LOGREG tile does not fit shared memory"); return BK_E_UNSUPPORTED; }
     dim3 grid((unsigned)((C + HLR_CT - 1) / HLR_CT), (unsigned)ns);
     prof_begin(BK_PROF_GRAD, st);
-    k_hlr_partial<T><<<grid, 256, smem, st>>>((const T*)m.d.X, (const T*)m.d.y, theta, C, N, Dx, D, rows, pg, pl);
+    if (grad)
+        k_hlr_partial<T, true><<<grid, 256, smem, st>>>((const T*)m.d.X, (const T*)m.d.y, theta, C, N, Dx, D, rows, pg, pl);
+    else
+        k_hlr_partial<T, false><<<grid, 256, smem, st>>>((const T*)m.d.X, (const T*)m.d.y, theta, C, N, Dx, D, rows, pg, pl);
     prof_end(BK_PROF_GRAD, st);
     BK_LAUNCH_CHECK();
     k_hlr_finish<T><<<(unsigned)((C * 32 + 255) / 256), 256, 0, st>>>(theta, pg, pl, C, Dx, D, ns, lp, grad);
@@ -226,10 +247,10 @@ static int hlr_eval_t(const Model& m, const T* theta, int64_t C, T* lp, T* grad,
 }
 
 int hlr_eval(const Model& m, const void* theta, int64_t C, void* lp, void* grad, void* ws, size_t ws_bytes,
-             cudaStream_t st) {
+             cudaStream_t st, bool precise) {
     if (m.d.dtype == BK_F64)
-        return hlr_eval_t<double>(m, (const double*)theta, C, (double*)lp, (double*)grad, ws, ws_bytes, st);
-    return hlr_eval_t<float>(m, (const float*)theta, C, (float*)lp, (float*)grad, ws, ws_bytes, st);
+        return hlr_eval_t<double>(m, (const double*)theta, C, (double*)lp, (double*)grad, ws, ws_bytes, st, true);
+    return hlr_eval_t<float>(m, (const float*)theta, C, (float*)lp, (float*)grad, ws, ws_bytes, st, precise);
 }
 
 }  // namespace bk

@@ -177,7 +177,7 @@ __global__ void k_dense_lp(const T* __restrict__ theta, const T* __restrict__ mu
 
 template <typename T>
 static int eval_t(const Model& m, const T* theta, int64_t C, T* lp, T* grad, void* ws,
-                  size_t ws_bytes, cudaStream_t st) {
+                  size_t ws_bytes, cudaStream_t st, bool precise) {
     const int D = (int)m.d.dims;
     if (C == 0) return BK_OK;
     const unsigned wblocks = (unsigned)((C * 32 + 255) / 256);
@@ -225,12 +225,14 @@ static int eval_t(const Model& m, const T* theta, int64_t C, T* lp, T* grad, voi
             return BK_OK;
         }
         case BK_MODEL_HIER_LOGREG:
-            return hlr_eval(m, theta, C, lp, grad, ws, ws_bytes, st);
+            return hlr_eval(m, theta, C, lp, grad, ws, ws_bytes, st, precise);
         default:
             set_error("model kind %d has no device evaluator", m.d.kind);
             return BK_E_UNSUPPORTED;
     }
 }
+
+bool model_has_fast_path(const Model& m) { return hlr_tc_enabled(m); }
 
 size_t model_eval_ws_bytes(const Model& m, int64_t C) {
     if (m.d.kind == BK_MODEL_HIER_LOGREG) return hlr_eval_ws_bytes(m, C);
@@ -243,10 +245,10 @@ size_t model_eval_ws_bytes(const Model& m, int64_t C) {
 }
 
 int model_eval(const Model& m, const void* theta, int64_t C, void* lp, void* grad, void* ws,
-               size_t ws_bytes, cudaStream_t st) {
+               size_t ws_bytes, cudaStream_t st, bool precise) {
     if (m.d.dtype == BK_F64)
-        return eval_t<double>(m, (const double*)theta, C, (double*)lp, (double*)grad, ws, ws_bytes, st);
-    return eval_t<float>(m, (const float*)theta, C, (float*)lp, (float*)grad, ws, ws_bytes, st);
+        return eval_t<double>(m, (const double*)theta, C, (double*)lp, (double*)grad, ws, ws_bytes, st, true);
+    return eval_t<float>(m, (const float*)theta, C, (float*)lp, (float*)grad, ws, ws_bytes, st, precise);
 }
 
 }  // namespace bk
@@ -257,7 +259,7 @@ extern "C" {
 
 size_t bk_model_workspace_bytes(const bk_model_desc* desc) {
     if (!desc) return 0;
-    return 256 + dense_tc_model_ws_bytes(*desc);  // bf16 splits of P, P*mu
+    return 256 + dense_tc_model_ws_bytes(*desc) + hlr_tc_model_ws_bytes(*desc);  // tensor-core operands
 }
 
 int bk_model_create(const bk_model_desc* desc, void* ws, size_t ws_bytes, void* stream,
@@ -296,6 +298,10 @@ int bk_model_create(const bk_model_desc* desc, void* ws, size_t ws_bytes, void* 
         int rc = dense_tc_prepare(m, ws, ws_bytes, (cudaStream_t)stream);
         if (rc) return rc;
     }
+    if (ws && ws_bytes >= hlr_tc_model_ws_bytes(*desc) && hlr_tc_model_ws_bytes(*desc) > 0) {
+        int rc = hlr_tc_prepare(m, ws, ws_bytes, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
     std::lock_guard<std::mutex> lk(g_mu);
     uint64_t h = g_next++;
     g_models[h] = m;
@@ -328,6 +334,14 @@ int bk_model_log_density_gradient(uint64_t handle, const void* theta, int64_t C,
     if (!m) return BK_E_HANDLE;
     BK_CHECK_ARG(theta && lp_out && C >= 0, "bk_model_log_density_gradient: bad argument");
     return model_eval(*m, theta, C, lp_out, grad_out, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int bk_model_log_density_gradient_fast(uint64_t handle, const void* theta, int64_t C, void* lp_out,
+                                       void* grad_out, void* ws, size_t ws_bytes, void* stream) {
+    const Model* m = get_model(handle);
+    if (!m) return BK_E_HANDLE;
+    BK_CHECK_ARG(theta && lp_out && C >= 0, "bk_model_log_density_gradient_fast: bad argument");
+    return model_eval(*m, theta, C, lp_out, grad_out, ws, ws_bytes, (cudaStream_t)stream, /*precise=*/false);
 }
 
 int bk_model_log_prior_likelihood(uint64_t handle, const void* theta, int64_t C,

@@ -272,8 +272,15 @@ int run_generic(const Model& m, GenArgs<T> p, int algo, int* cache_valid, void* 
     if (rc) return rc;
     const unsigned blocks = (unsigned)((p.C * 32 + 255) / 256);
     const bool need_grad = algo != ALGO_MHRW;
+    const bool fast = algo == ALGO_HMC && model_has_fast_path(m);
     if (!cache_valid || !*cache_valid) {
-        rc = model_eval(m, p.theta, p.C, p.lp, need_grad ? p.grad : nullptr, ews, ebytes, st);
+        if (fast) {   // same convention as inside the loop: tensor-core gradient, precise density
+            rc = model_eval(m, p.theta, p.C, p.lp, p.grad, ews, ebytes, st, false);
+            if (rc) return rc;
+            rc = model_eval(m, p.theta, p.C, p.lp, nullptr, ews, ebytes, st, true);
+        } else {
+            rc = model_eval(m, p.theta, p.C, p.lp, need_grad ? p.grad : nullptr, ews, ebytes, st);
+        }
         if (rc) return rc;
         if (cache_valid) *cache_valid = 1;
     }
@@ -282,7 +289,18 @@ int run_generic(const Model& m, GenArgs<T> p, int algo, int* cache_valid, void* 
             k_hmc_begin<T><<<blocks, 256, 0, st>>>(p, t);
             BK_LAUNCH_CHECK();
             for (int s = 0; s < p.L; ++s) {
-                rc = model_eval(m, p.q, p.C, p.lp_q, p.grad_q, ews, ebytes, st);
+                // Gradients may come from the plugin's reduced-precision tensor-core path at
+                // EVERY step: leapfrog with any deterministic gradient function is reversible
+                // and volume preserving (the endpoint gradient is also what the next
+                // trajectory starts from).  Only the log density that enters the Hamiltonian
+                // must be precise: at the endpoint it is evaluated separately, density only.
+                if (fast) {
+                    rc = model_eval(m, p.q, p.C, p.lp_q, p.grad_q, ews, ebytes, st, /*precise=*/false);
+                    if (rc) return rc;
+                    if (s + 1 == p.L) rc = model_eval(m, p.q, p.C, p.lp_q, nullptr, ews, ebytes, st, true);
+                } else {
+                    rc = model_eval(m, p.q, p.C, p.lp_q, p.grad_q, ews, ebytes, st, true);
+                }
                 if (rc) return rc;
                 if (s + 1 < p.L) {
                     k_hmc_step<T><<<blocks, 256, 0, st>>>(p);

@@ -67,7 +67,7 @@ class DeviceModel:
     def dims(self) -> int:
         return self._dims
 
-    def _eval(self, theta, want_grad):
+    def _eval(self, theta, want_grad, fast=False):
         th = to_dev(theta, self.dtype, self.device)
         single = th.dim() == 1
         th2 = th.reshape(1, -1) if single else th
@@ -79,8 +79,9 @@ class DeviceModel:
         lib = L.lib()
         wp, wn = self._ws.get(lib.bk_model_eval_workspace_bytes(self._handle, Cn))
         with torch.cuda.device(self.device):
-            L.check(lib.bk_model_log_density_gradient(self._handle, th2.data_ptr(), Cn, lp.data_ptr(),
-                                                      ptr(g), wp, wn, stream_ptr(self.device)))
+            fn = lib.bk_model_log_density_gradient_fast if fast else lib.bk_model_log_density_gradient
+            L.check(fn(self._handle, th2.data_ptr(), Cn, lp.data_ptr(), ptr(g), wp, wn,
+                       stream_ptr(self.device)))
         if single:
             return float(lp[0]), (g[0] if want_grad else None)
         return lp, g
@@ -88,8 +89,10 @@ class DeviceModel:
     def log_density(self, theta):
         return self._eval(theta, False)[0]
 
-    def log_density_gradient(self, theta):
-        return self._eval(theta, True)
+    def log_density_gradient(self, theta, fast: bool = False):
+        """``fast=True``: the reduced-precision (tensor-core) evaluation the samplers use
+        for interior leapfrog steps, where the plugin has one."""
+        return self._eval(theta, True, fast)
 
 
 class IsoGauss(DeviceModel):

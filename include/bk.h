@@ -123,6 +123,13 @@ BK_API size_t bk_model_eval_workspace_bytes(uint64_t handle, int64_t C);
  * grad [C,D] (grad may be NULL).  hmc.py:38,45,50; mala.py:31,46 */
 BK_API int bk_model_log_density_gradient(uint64_t handle, const void* theta, int64_t C, void* lp_out,
                                   void* grad_out, void* ws, size_t ws_bytes, void* stream);
+/* Same contract, but the plugin may answer with its reduced-precision tensor-core path
+ * (bf16 operands, fp32 accumulate).  This is what the samplers use for INTERIOR leapfrog
+ * gradients -- any deterministic gradient keeps the leapfrog map reversible and volume
+ * preserving; everything that enters a Metropolis test uses the precise evaluation above. */
+BK_API int bk_model_log_density_gradient_fast(uint64_t handle, const void* theta, int64_t C,
+                                       void* lp_out, void* grad_out, void* ws, size_t ws_bytes,
+                                       void* stream);
 /* log_prior / log_likelihood (smc.py:29-33), GAUSS_PRIOR_LIK only */
 BK_API int bk_model_log_prior_likelihood(uint64_t handle, const void* theta, int64_t C,
                                   void* log_prior_out, void* log_lik_out, void* stream);

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bayes_kit_b200 as bk
 HBM = 6548.5  # GB/s measured (MEASURED_PEAKS.json)
-which = sys.argv[1:] or ["c1", "c1mala", "c4", "c5"]
+which = sys.argv[1:] or ["c1", "c1mala", "c2mala", "c3", "drghmc", "c4", "c5"]
 
 def timed(fn, reps=5, warm=2):
     for _ in range(warm): fn()
@@ -34,6 +34,33 @@ if "c1mala" in which:
     print(json.dumps({"workload": f"MALA iso D={D} C={C} n={n}/launch fp32", "ms_per_launch": ms,
           "chain_steps_per_s": steps, "GBps_algorithmic(804B/step)": steps * 804 / 1e9,
           "hbm_frac": steps * 804 / 1e9 / HBM}), flush=True)
+if "c2mala" in which:
+    from oracle.models import DensePrecGauss
+    D, C = 1000, 65536
+    model = bk.DensePrecGauss(DensePrecGauss.c2_precision(D, 0))
+    s = bk.MALA(model, 2e-3, chains=C, seed=0)
+    ms = timed(lambda: s.sample_n(1), reps=10, warm=3)
+    print(json.dumps({"workload": f"c2 MALA dense D={D} C={C} eps=2e-3 fp32 (generic engine + tcgen05 3-pass gradient)",
+          "ms_per_draw": ms, "chain_steps_per_s": C / (ms * 1e-3), "accept": float(s.last_accept.float().mean()),
+          "grad_TFLOPs(2CD^2)": 2.0 * C * D * D / (ms * 1e-3) / 1e12}), flush=True)
+if "c3" in which:
+    from oracle.models import HierLogReg
+    N, Dx, C = 100_000, 100, 1024
+    X, y = HierLogReg.c3_data(N, Dx, seed=0)
+    model = bk.HierLogReg(X, y)
+    th0 = np.random.default_rng(1).normal(size=(C, Dx + 2)) * 0.1
+    s = bk.HMCDiag(model, 0.01, 10, init=th0, seed=0)
+    ms = timed(lambda: s.sample_n(1), reps=3, warm=1)
+    print(json.dumps({"workload": f"c3 HMCDiag hier-logreg N={N} Dx={Dx} C={C}/GPU L=10 eps=0.01 fp32 (CUDA-core fused evaluator)",
+          "ms_per_draw": ms, "chain_steps_per_s": C / (ms * 1e-3), "accept": float(s.last_accept.float().mean()),
+          "grad_evals_per_s": 10 * C / (ms * 1e-3), "TFLOPs(4NDx per grad)": 10 * C * 4.0 * N * Dx / (ms * 1e-3) / 1e12}), flush=True)
+if "drghmc" in which:
+    D, C, n = 100, 262144, 10
+    s = bk.DrGhmcDiag(bk.IsoGauss(D), 2, [0.6, 0.2], [5, 10], 0.5, chains=C, seed=0)
+    ms = timed(lambda: s.sample_n(n))
+    print(json.dumps({"workload": f"DrGhmcDiag iso D={D} K=2 eps=(0.6,0.2) counts=(5,10) damping=0.5 C={C} n={n}/launch fp32",
+          "ms_per_launch": ms, "chain_steps_per_s": C * n / (ms * 1e-3),
+          "move_rate": float(s.last_accept.float().mean())}), flush=True)
 if "c4" in which:
     D, M, T = 50, 1_000_000, 100
     mu = np.random.default_rng(0).normal(size=D)

@@ -120,3 +120,34 @@ def test_tc_posterior_moments(bk):
     n_eff = 2048 * 200 / 4.0   # conservative: |lag-1 autocorrelation| of x and x^2 is < 0.6
     assert np.all(np.abs(d.mean(0)) <= 4 * np.sqrt(var / n_eff) + 1e-3)
     assert np.all(np.abs(d.var(0, ddof=1) - var) <= 4 * var * np.sqrt(2 / n_eff) + 1e-3)
+
+
+def test_logreg_tc_gradient_and_hmc(bk):
+    """tcgen05 path of the hierarchical logistic regression plugin (interior leapfrog
+    gradients, bf16 operands): gradient within bf16 tolerance of the fp64 numpy model;
+    an fp32 HMC draw (tensor-core interior steps + fp32 CUDA-core endpoint) lands within
+    the trajectory tolerance of the fp64 oracle with the same accept decisions."""
+    from oracle.models import HierLogReg
+    rng = np.random.default_rng(0)
+    for (N, Dx, C) in [(1000, 37, 70), (5000, 100, 300), (129, 5, 3)]:
+        X, y = HierLogReg.c3_data(N, Dx, seed=1)
+        om = HierLogReg(X, y)
+        th = (rng.normal(size=(C, Dx + 2)) * 0.4).astype(np.float32).astype(np.float64)
+        dm = bk.HierLogReg(X, y, dtype=torch.float32)
+        lp, g = dm.log_density_gradient(th, fast=True)
+        want = [om.log_density_gradient(t) for t in th]
+        wl, wg = np.array([w[0] for w in want]), np.stack([w[1] for w in want])
+        assert np.abs(np_(g) - wg).max() <= 1e-2 * np.abs(wg).max(), np.abs(np_(g) - wg).max() / np.abs(wg).max()
+        np.testing.assert_allclose(np_(lp), wl, rtol=5e-3, atol=0.5)
+    N, Dx, C, L, eps = 5000, 100, 200, 8, 0.01
+    X, y = HierLogReg.c3_data(N, Dx, seed=2)
+    th0 = (rng.normal(size=(C, Dx + 2)) * 0.2).astype(np.float32).astype(np.float64)
+    zs = rng.standard_normal((1, C, Dx + 2)).astype(np.float32).astype(np.float64)
+    us = rng.random((1, C)).astype(np.float32).astype(np.float64)
+    od, ol, oa = osm.hmc_diag_batch(HierLogReg(X, y), th0, zs, us, eps, L)
+    s = bk.HMCDiag(bk.HierLogReg(X, y, dtype=torch.float32), eps, L, init=th0)
+    d, l = s.sample_n(1, normals=zs, uniforms=us)
+    a = np_(s.last_accept)[0].astype(bool)
+    assert (a != oa[0]).mean() <= 0.03
+    same = a == oa[0]
+    assert np.abs(np_(d)[0][same] - od[0][same]).max() <= 2e-2
