@@ -272,7 +272,7 @@ bool hlr_tc_enabled(const Model& m) {
 
 int hlr_tc_splits(int64_t C, int64_t N) {
     const int64_t ctiles = (C + CT - 1) / CT;
-    int64_t want = (148 + ctiles - 1) / ctiles;
+    int64_t want = 148 / ctiles;   // one CTA per SM (200 KB of shared memory): stay within ONE wave
     const int64_t max_split = (N + NT - 1) / NT;
     if (want > max_split) want = max_split;
     return (int)(want < 1 ? 1 : want);
