@@ -104,7 +104,77 @@ class ChainSampler:
             return (draws[:, 0] if keep_draws else None), logp[:, 0]
         return draws, logp
 
-    def _launch(self, n, rng, out):  # pragma: no cover - overridden
+    def sample_host(self, theta_host=None, out=None, chunk_chains: Optional[int] = None):
+        """One draw of every chain with HOST buffers, pipelined over chain chunks.
+
+        The reference's ``sample()`` hands back host arrays (hmc.py:63); this is
+        that call for C lockstep chains without serialising on PCIe: chains are
+        cut into chunks and chunk k's device->host copy of its draw, chunk
+        k+1's kernels and chunk k+2's host->device copy of its state run
+        concurrently on three streams.  Chunking cannot change the result --
+        Philox is keyed by the global chain id.
+
+        theta_host  [C, D] host tensor (pinned for overlap): the chain state is
+                    loaded from it first (and the cached log density / gradient
+                    recomputed); None keeps the device-resident state.
+        out         (draw_host [C, D], logp_host [C]) pinned tensors to fill;
+                    allocated (pinned) when None.
+        Returns (draw_host, logp_host), complete on return; ``theta`` holds the
+        same draw on device and ``last_accept`` the accept flags.
+        """
+        if self._single:
+            raise ValueError("sample_host is the batched surface: construct with init [C, D] or chains=C")
+        C_, D = self._C, self._dim
+        if out is None:
+            out = (torch.empty(C_, D, dtype=self.dtype).pin_memory(),
+                   torch.empty(C_, dtype=self.dtype).pin_memory())
+        draw_h, logp_h = out
+        for name, t, shape in (("theta_host", theta_host, (C_, D)), ("out[0]", draw_h, (C_, D)),
+                               ("out[1]", logp_h, (C_,))):
+            if t is not None and (tuple(t.shape) != shape or t.dtype != self.dtype or t.is_cuda
+                                  or not t.is_contiguous()):
+                raise ValueError(f"{name} must be a contiguous host {self.dtype} tensor of shape {shape}")
+        if chunk_chains is None:
+            # 37 chain-tiles of 256 (two full waves of the 148-CTA gradient GEMM) at D ~ 1000
+            chunk_chains = max(256, int(round(9472 * 1000 / max(D, 1) / 256)) * 256)
+        chunk_chains = max(1, min(int(chunk_chains), C_))
+        if getattr(self, "_hs", None) is None:
+            self._hs = tuple(torch.cuda.Stream(self.device) for _ in range(3))
+            self._h_draw = torch.empty(C_, D, dtype=self.dtype, device=self.device)
+            self._h_logp = torch.empty(C_, dtype=self.dtype, device=self.device)
+            self._h_acc = torch.empty(C_, dtype=torch.int32, device=self.device)
+        s_in, s_run, s_out = self._hs
+        cur = torch.cuda.current_stream(self.device)
+        for s in self._hs:
+            s.wait_stream(cur)
+        # state loaded from the host (or never evaluated): the (logp, grad) cache is stale
+        stale = theta_host is not None or not self._cache_valid.value
+        for c0 in range(0, C_, chunk_chains):
+            cn = min(chunk_chains, C_ - c0)
+            valid = L.i32(0 if stale else 1)
+            if theta_host is not None:
+                with torch.cuda.stream(s_in):
+                    self._theta[c0:c0 + cn].copy_(theta_host[c0:c0 + cn], non_blocking=True)
+                s_run.wait_stream(s_in)
+            with torch.cuda.stream(s_run):
+                rng = make_rng(self._seed, self._t, self._chain_offset + c0, None, None, self._n_uniform)
+                o = L.DrawOut(self._h_draw[c0:].data_ptr(), self._h_logp[c0:].data_ptr(),
+                              self._h_acc[c0:].data_ptr())
+                self._launch(1, rng, o, c0, cn, valid)
+                done = torch.cuda.Event()
+                done.record(s_run)
+            s_out.wait_event(done)
+            with torch.cuda.stream(s_out):
+                draw_h[c0:c0 + cn].copy_(self._h_draw[c0:c0 + cn], non_blocking=True)
+                logp_h[c0:c0 + cn].copy_(self._h_logp[c0:c0 + cn], non_blocking=True)
+        self._t += 1
+        self.last_accept = self._h_acc
+        self._cache_valid.value = 1              # every chunk refreshed its slice of the cache
+        cur.wait_stream(s_run)
+        s_out.synchronize()
+        return draw_h, logp_h
+
+    def _launch(self, n, rng, out, c0=0, cn=None, cache_valid=None):  # pragma: no cover - overridden
         raise NotImplementedError
 
     def _need_grad_cache(self):

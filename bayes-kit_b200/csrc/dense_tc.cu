@@ -6,10 +6,14 @@
 // tile [256 chains x 64 k], both K-major with the 128-byte swizzle, staged by a
 // 4-deep TMA/mbarrier ring.  TMEM lanes are DIMS and TMEM columns are CHAINS,
 // so in the epilogue a warp's 32 lanes touch 32 consecutive dims of one chain:
-// every global access of the fused leapfrog update
-//        r += eps * m * g ;  q += eps * r ;  q_bf16(next operand) = bf16(q)
-// is a coalesced 128-byte row segment, straight from registers (no smem
-// staging).  The accumulator is double-buffered (2 x 256 TMEM columns) so the
+// every global access of the fused leapfrog update is a coalesced 128-byte row
+// segment.  The update is the leapfrog recursion in POSITION form (Stormer-
+// Verlet): kick r += eps*m*g and drift q += eps*r combine to
+//        q_{n+1} = q_n + ((q_n - q_{n-1}) + eps^2 * m * g(q_n))
+// so the momentum never exists in memory: a step reads q_n, q_{n-1} and writes
+// q_{n+1} over q_{n-1} (12 B fp32 per element instead of 16) plus the bf16
+// operand for the next GEMM; eps*r_{n+1/2} = q_{n+1} - q_n is recovered at the
+// trajectory end, where the Hamiltonian needs it.  The accumulator is double-buffered (2 x 256 TMEM columns) so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Precision: interior leapfrog gradients use bf16 operands (the leapfrog map
@@ -187,8 +191,8 @@ struct StepArgs {
     float eps;
     const float* metric;  // [D] or NULL
     const float* cvec;    // [D] P*mu or NULL
-    float* r;             // tile-blocked (STEP: in/out)
-    float* q;             // tile-blocked (STEP: in/out)
+    float* q_prev;        // tile-blocked (STEP: q_{n-1} in, q_{n+1} out)
+    const float* q_cur;   // tile-blocked (STEP: q_n, read only)
     __nv_bfloat16* q_hi_next;  // [C, Dp] (STEP)
     __nv_bfloat16* q_lo_next;  // [C, Dp] or NULL
     float* g_out;         // [C, D] row-major, or tile-blocked when g_blocked
@@ -345,7 +349,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
             // r and q through a private cp.async ring in shared memory (EDEPTH-1 chunks =
             // 12 KB per warp, 96 KB per SM in flight, no registers held, prefetch runs
             // across tile boundaries and ahead of the accumulator), then updates from
-            // registers:  r += eps*m*g ; q += eps*r ; q_hi(next operand) = bf16(q).
+            // registers:  q_next = q + ((q - q_prev) + eps^2*m*g) ; q_hi(next operand) = bf16(q_next).
             constexpr int NC = NCH * 32 / CWID;                 // chunks per warp per tile
             const bool no_mem = (a.debug & 2) != 0;
             const uint32_t ring = ering + (uint32_t)(warp - 2) * (EDEPTH * ECHUNK_BYTES);
@@ -368,8 +372,8 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                         const int row = it * 4 + row_in;
                         const int64_t eo = e0 + (int64_t)row * BM + seg * 4;
                         const uint32_t so = (uint32_t)(row * 128 + seg * 16);
-                        cp_async16(dst + so, a.r + eo);
-                        cp_async16(dst + CWID * 128 + so, a.q + eo);
+                        cp_async16(dst + so, a.q_prev + eo);
+                        cp_async16(dst + CWID * 128 + so, a.q_cur + eo);
                     }
                 }
                 cp_async_commit();
@@ -383,15 +387,13 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                 const int d = m_tile * BM + quarter * 32 + lane;
                 const bool d_ok = d < a.D;
                 const float cv = (a.cvec && d_ok) ? a.cvec[d] : 0.0f;
-                const float em = a.eps * ((a.metric && d_ok) ? a.metric[d] : 1.0f);
-                const float eps = a.eps;
+                const float em2 = a.eps * a.eps * ((a.metric && d_ok) ? a.metric[d] : 1.0f);
                 const uint32_t t0 = tmem_base + (uint32_t)acc * BN + ((uint32_t)(quarter * 32) << 16) +
                                     (uint32_t)(half * NCH * 32);
                 const int64_t cbase = n_tile * BN + half * NCH * 32;
                 const bool full_tile = d_ok && cbase + NCH * 32 <= a.C;
                 const int64_t e0 = blk_index(cbase, d, a.m_tiles);
-                float* rw = a.r + e0;
-                float* qw = a.q + e0;
+                float* qw = a.q_prev + e0;      // q_{n+1} replaces q_{n-1}
                 const int64_t b0i = box_index(cbase, d, a.kblocks, BN);
                 __nv_bfloat16* hw = a.q_hi_next + b0i;
                 __nv_bfloat16* lw = a.q_lo_next ? a.q_lo_next + b0i : nullptr;
@@ -408,14 +410,13 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                     const int64_t o = (int64_t)ch * CWID * BM, ob = (int64_t)ch * CWID * BK;
 #pragma unroll
                     for (int j = 0; j < CWID; ++j) {
-                        float rj, qj;
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(rj) : "r"(src + j * 128));
+                        float pj, qj;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pj) : "r"(src + j * 128));
                         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qj) : "r"(src + CWID * 128 + j * 128));
                         if (!no_mem && (full_tile || (d_ok && cbase + ch * CWID + j < a.C))) {
                             const float gj = cv - __uint_as_float(v[j]);
-                            const float rn = fmaf(em, gj, rj);    // r += eps * m * g
-                            const float qn = fmaf(eps, rn, qj);   // q += eps * r
-                            __stcs(rw + o + (int64_t)j * BM, rn);
+                            // eps*r_{n+1/2} = eps*r_{n-1/2} + eps^2*m*g ;  q_{n+1} = q_n + eps*r_{n+1/2}
+                            const float qn = qj + fmaf(em2, gj, qj - pj);
                             __stcs(qw + o + (int64_t)j * BM, qn);
                             const __nv_bfloat16 hi = __float2bfloat16_rn(qn);
                             hw[ob + (int64_t)j * BK] = hi;
@@ -481,12 +482,12 @@ __global__ void k_split_rows(const float* __restrict__ x, int64_t C, int D, int 
 // ---- HMC begin / end around the tensor-core steps (fp32) ----------------------------
 struct HmcTcArgs {
     float *theta, *lp, *grad;   // state
-    float *q, *r, *gq, *h0;     // workspace
+    float *q, *qm, *gq, *h0;    // workspace: begin writes q_1 -> q, q_0 -> qm; end reads q_L, q_{L-1}
     __nv_bfloat16 *q_hi, *q_lo; // operand for the first GEMM
     const float *metric, *mu;
     int64_t C;
     int D, Dp, L, m_tiles;
-    float eps, half_eps;
+    float eps, half_eps, inv_eps;
     bk_rng rng;
     float *draws, *logp;
     int32_t* accept;
@@ -561,8 +562,8 @@ __global__ void __launch_bounds__(256) k_hmc_begin_tc(HmcTcArgs p, int64_t t, in
             hi[i] = __float2bfloat16_rn(q[i]);
             lo[i] = __float2bfloat16_rn(q[i] - __bfloat162float(hi[i]));
         }
-        const int64_t bo = blk_index(c, e, p.m_tiles);   // r, q are tile-blocked
-        st4<true>(p.r + bo, 0, 4, r);
+        const int64_t bo = blk_index(c, e, p.m_tiles);   // q_0, q_1 are tile-blocked
+        st4<true>(p.qm + bo, 0, 4, th);
         st4<true>(p.q + bo, 0, 4, q);
         const int64_t xo = box_index(c, e, p.Dp / BK, BN);   // e % 4 == 0: stays inside one box row
         st4_bf16<true>(p.q_hi + xo, 0, 4, hi);
@@ -583,17 +584,18 @@ __global__ void __launch_bounds__(256) k_hmc_end_tc(HmcTcArgs p, int64_t t) {
 #pragma unroll 2
     for (int b = lane; 4 * b < D; b += 32) {
         const int e = 4 * b;
-        float g[4], r[4], q[4], m[4] = {1.f, 1.f, 1.f, 1.f}, mu[4] = {0.f, 0.f, 0.f, 0.f};
-        const int64_t bo = blk_index(c, e, p.m_tiles);   // gq, r, q are tile-blocked
+        float g[4], qm[4], q[4], m[4] = {1.f, 1.f, 1.f, 1.f}, mu[4] = {0.f, 0.f, 0.f, 0.f};
+        const int64_t bo = blk_index(c, e, p.m_tiles);   // gq, q_{L-1}, q_L are tile-blocked
         ld4<true>(p.gq + bo, 0, 4, g);
-        ld4<true>(p.r + bo, 0, 4, r);
+        ld4<true>(p.qm + bo, 0, 4, qm);
         ld4<true>(p.q + bo, 0, 4, q);
         if (p.metric) ld4<VEC>(p.metric, e, D, m);
         if (p.mu) ld4<VEC>(p.mu, e, D, mu);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (e + i >= D) break;                                // blocked arrays carry pad dims
-            const float rf = r[i] + p.half_eps * (m[i] * g[i]);   // forward half kick (hmc.py:52)
+            // r_{L-1/2} = (q_L - q_{L-1}) / eps, then the forward half kick (hmc.py:52)
+            const float rf = fmaf(q[i] - qm[i], p.inv_eps, p.half_eps * (m[i] * g[i]));
             kin = fmaf(rf, m[i] * rf, kin);
             dot = fmaf(q[i] - mu[i], g[i], dot);                  // log p(q) = 0.5 (q-mu).g
         }
@@ -783,8 +785,7 @@ int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* 
     const size_t n = (size_t)align_up((size_t)C, tc::BN) * m.Dp;   // tile-blocked, padded
     const size_t nb = n;                                           // box-blocked bf16, padded
     Arena ar(ws, ws_bytes);
-    float* q = ar.take<float>(n);
-    float* r = ar.take<float>(n);
+    float* qbuf[2] = {ar.take<float>(n), ar.take<float>(n)};   // q_{n-1} / q_n, roles swap every step
     float* gq = ar.take<float>(n);
     float* h0 = ar.take<float>(C);
     __nv_bfloat16* qhi[2] = {ar.take<__nv_bfloat16>(nb), ar.take<__nv_bfloat16>(nb)};
@@ -809,16 +810,16 @@ int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* 
     }
     tc::HmcTcArgs h;
     memset(&h, 0, sizeof(h));
-    h.theta = theta; h.lp = lp; h.grad = grad; h.q = q; h.r = r; h.gq = gq; h.h0 = h0;
+    h.theta = theta; h.lp = lp; h.grad = grad; h.gq = gq; h.h0 = h0;
     h.metric = metric; h.mu = (const float*)m.d.mu; h.C = C; h.D = D; h.Dp = (int)m.Dp; h.L = L;
     h.m_tiles = (int)(m.Dp / tc::BM);
-    h.eps = (float)eps; h.half_eps = (float)(0.5 * eps); h.rng = *rng;
+    h.eps = (float)eps; h.half_eps = (float)(0.5 * eps); h.inv_eps = (float)(1.0 / eps); h.rng = *rng;
     h.draws = (float*)out.draws; h.logp = (float*)out.logp; h.accept = out.accept;
     tc::StepArgs a;
     memset(&a, 0, sizeof(a));
     a.C = C; a.D = D; a.Dp = (int)m.Dp;
     a.m_tiles = (int)(m.Dp / tc::BM); a.n_tiles = (C + tc::BN - 1) / tc::BN; a.kblocks = (int)(m.Dp / tc::BK);
-    a.eps = (float)eps; a.metric = metric; a.cvec = (const float*)m.Pmu; a.r = r; a.q = q; a.g_out = gq;
+    a.eps = (float)eps; a.metric = metric; a.cvec = (const float*)m.Pmu; a.g_out = gq;
     a.g_blocked = 1;
     { const char* e = getenv("BK_TC_DEBUG"); a.debug = e ? atoi(e) : 0; }
     const unsigned wblocks = (unsigned)((C * 32 + 255) / 256);
@@ -827,6 +828,7 @@ int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* 
                      al16(out.draws) && (rng->mode != BK_RNG_INJECTED || al16(rng->normals));
     for (int64_t t = 0; t < n_draws; ++t) {
         h.q_hi = qhi[0]; h.q_lo = qlo;
+        h.qm = qbuf[0]; h.q = qbuf[1];              // begin: q_0 = theta -> qm, q_1 -> q
         if (vec) tc::k_hmc_begin_tc<true><<<wblocks, 256, 0, st>>>(h, t, L == 1 ? 1 : 0);
         else tc::k_hmc_begin_tc<false><<<wblocks, 256, 0, st>>>(h, t, L == 1 ? 1 : 0);
         BK_LAUNCH_CHECK();
@@ -835,9 +837,11 @@ int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* 
             a.mode = TC_MODE_STEP; a.n_pass = 1;
             a.q_hi_next = qhi[cur ^ 1];
             a.q_lo_next = (s == L - 1) ? qlo : nullptr;
+            a.q_prev = h.qm; a.q_cur = h.q;         // q_{s+1} overwrites q_{s-1}
             rc = tc::launch_tc(m, a, qhi[cur], nullptr, st);
             if (rc) return rc;
             cur ^= 1;
+            float* t2 = h.qm; h.qm = h.q; h.q = t2;
         }
         // endpoint gradient with the 3-pass split: enters the Hamiltonian and the cache
         a.mode = TC_MODE_GRAD; a.n_pass = 3; a.q_hi_next = nullptr; a.q_lo_next = nullptr;

@@ -95,6 +95,10 @@ class DrGhmcDiag(ChainSampler):
                 raise ValueError(f"each {item} in {name} must be positive, but found {item} of {v} "
                                  f"at index {idx}")
 
+    def sample_host(self, *a, **k):
+        raise NotImplementedError("sample_host: DrGhmcDiag keeps a persistent momentum per chain; "
+                                  "use sample()/sample_n() with device tensors")
+
     def _launch(self, n, rng, out):
         lib = L.lib()
         used = torch.empty(n, self._C, dtype=torch.int32, device=self.device)

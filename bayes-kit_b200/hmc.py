@@ -44,11 +44,12 @@ class HMCDiag(ChainSampler):
                 raise ValueError(f"metric_diag must have {self._dim} entries")
             self._metric = m
 
-    def _launch(self, n, rng, out):
+    def _launch(self, n, rng, out, c0=0, cn=None, cache_valid=None):
         lib = L.lib()
         self._need_grad_cache()
+        cn = self._C if cn is None else cn
         wp, wn = self._ws.get(lib.bk_hmc_diag_workspace_bytes(self._model.handle, self._C))
         L.check(lib.bk_hmc_diag_sample(
-            self._model.handle, self._theta.data_ptr(), self._lp.data_ptr(), self._grad.data_ptr(),
-            C.byref(self._cache_valid), self._C, self._stepsize, self._steps, ptr(self._metric), n,
-            C.byref(rng), C.byref(out), wp, wn, stream_ptr(self.device)))
+            self._model.handle, self._theta[c0:].data_ptr(), self._lp[c0:].data_ptr(),
+            self._grad[c0:].data_ptr(), C.byref(self._cache_valid if cache_valid is None else cache_valid), cn, self._stepsize,
+            self._steps, ptr(self._metric), n, C.byref(rng), C.byref(out), wp, wn, stream_ptr(self.device)))

@@ -22,11 +22,12 @@ class MALA(ChainSampler):
         if not self._epsilon > 0:
             raise ValueError(f"epsilon must be positive, got {epsilon}")
 
-    def _launch(self, n, rng, out):
+    def _launch(self, n, rng, out, c0=0, cn=None, cache_valid=None):
         lib = L.lib()
         self._need_grad_cache()
+        cn = self._C if cn is None else cn
         wp, wn = self._ws.get(lib.bk_mala_workspace_bytes(self._model.handle, self._C))
         L.check(lib.bk_mala_sample(
-            self._model.handle, self._theta.data_ptr(), self._lp.data_ptr(), self._grad.data_ptr(),
-            C.byref(self._cache_valid), self._C, self._epsilon, n, C.byref(rng), C.byref(out), wp, wn,
-            stream_ptr(self.device)))
+            self._model.handle, self._theta[c0:].data_ptr(), self._lp[c0:].data_ptr(),
+            self._grad[c0:].data_ptr(), C.byref(self._cache_valid if cache_valid is None else cache_valid), cn, self._epsilon, n,
+            C.byref(rng), C.byref(out), wp, wn, stream_ptr(self.device)))

@@ -72,13 +72,14 @@ class MetropolisHastings(ChainSampler):
         self._proposal_fn = prop
         self._transition_lp_fn = transition_lp_fn
 
-    def _launch(self, n, rng, out):
+    def _launch(self, n, rng, out, c0=0, cn=None, cache_valid=None):
         lib = L.lib()
+        cn = self._C if cn is None else cn
         wp, wn = self._ws.get(lib.bk_mh_rw_workspace_bytes(self._model.handle, self._C))
         L.check(lib.bk_mh_rw_sample(
-            self._model.handle, self._theta.data_ptr(), self._lp.data_ptr(), C.byref(self._cache_valid),
-            self._C, self._proposal_fn.scale, self._hastings, n, C.byref(rng), C.byref(out), wp, wn,
-            stream_ptr(self.device)))
+            self._model.handle, self._theta[c0:].data_ptr(), self._lp[c0:].data_ptr(),
+            C.byref(self._cache_valid if cache_valid is None else cache_valid), cn, self._proposal_fn.scale, self._hastings, n,
+            C.byref(rng), C.byref(out), wp, wn, stream_ptr(self.device)))
 
 
 class Metropolis(MetropolisHastings):

@@ -252,12 +252,9 @@ def main():
     e2e_steps = max(3, min(args.steps, 10))
 
     def e2e_step(k):
-        sampler._theta.copy_(host_buf[k & 1], non_blocking=True)   # H2D: chain state
-        sampler._cache_valid.value = 0                             # state came from the host
-        th, lp = sampler.sample()
-        host_buf[(k + 1) & 1].copy_(th, non_blocking=True)         # D2H: the draw
-        host_lp.copy_(lp, non_blocking=True)                       # D2H: its log density
-        torch.cuda.current_stream().synchronize()
+        # public API: chain state in from host buffer k&1, draw + log density out to the other;
+        # H2D, kernels and D2H of successive chain chunks overlap on three streams
+        sampler.sample_host(host_buf[k & 1], out=(host_buf[(k + 1) & 1], host_lp))
 
     for k in range(2):
         e2e_step(k)
