@@ -122,6 +122,14 @@ int mala_t(const Model& m, void* theta, void* lp, void* grad, int32_t* valid, in
         return launch_sep_sampler<T>(a, st);
     }
     BK_CHECK_ARG(lp && grad, "bk_mala_sample: lp_cache/grad_cache are required for this model");
+    if constexpr (sizeof(T) == 4) {
+        // theta + eps g + sqrt(2 eps) z is one leapfrog step of size h = sqrt(2 eps) from momentum z,
+        // and the Hastings ratio equals the Hamiltonian difference: begin -> split-precision
+        // tcgen05 gradient -> accept, three launches per draw
+        if (dense_tc_enabled(m))
+            return dense_tc_hmc(m, (float*)theta, (float*)lp, (float*)grad, valid, C, sd, 1, nullptr, n, rng,
+                                out, ws, wsb, st, /*report_lp=*/true);
+    }
     GenArgs<T> p;
     fill_gen(p, m, theta, lp, grad, C, nullptr, n, rng, out);
     p.eps = (T)eps;

@@ -491,6 +491,7 @@ struct HmcTcArgs {
     bk_rng rng;
     float *draws, *logp;
     int32_t* accept;
+    int out_lp;                 // 1: report log p(theta) (MALA, mala.py:66) instead of the joint (hmc.py:63)
 };
 
 // One warp per chain, lane-strided blocks of 4 elements (the Philox block
@@ -629,8 +630,9 @@ __global__ void __launch_bounds__(256) k_hmc_end_tc(HmcTcArgs p, int64_t t) {
         if (dr) st4<VEC>(dr, e, D, v);
     }
     if (lane == 0) {
+        const float lp_old = p.lp[c];
         if (acc) p.lp[c] = lpq;
-        if (p.logp) p.logp[t * p.C + c] = acc ? h1 : h0;
+        if (p.logp) p.logp[t * p.C + c] = p.out_lp ? (acc ? lpq : lp_old) : (acc ? h1 : h0);
         if (p.accept) p.accept[t * p.C + c] = acc ? 1 : 0;
     }
 }
@@ -780,7 +782,7 @@ int dense_tc_grad(const Model& m, const float* theta, int64_t C, float* grad, vo
 
 int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* cache_valid, int64_t C,
                  double eps, int L, const float* metric, int64_t n_draws, const bk_rng* rng,
-                 const bk_draw_out& out, void* ws, size_t ws_bytes, cudaStream_t st) {
+                 const bk_draw_out& out, void* ws, size_t ws_bytes, cudaStream_t st, bool report_lp) {
     const int D = (int)m.d.dims;
     const size_t n = (size_t)align_up((size_t)C, tc::BN) * m.Dp;   // tile-blocked, padded
     const size_t nb = n;                                           // box-blocked bf16, padded
@@ -815,6 +817,7 @@ int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* 
     h.m_tiles = (int)(m.Dp / tc::BM);
     h.eps = (float)eps; h.half_eps = (float)(0.5 * eps); h.inv_eps = (float)(1.0 / eps); h.rng = *rng;
     h.draws = (float*)out.draws; h.logp = (float*)out.logp; h.accept = out.accept;
+    h.out_lp = report_lp ? 1 : 0;
     tc::StepArgs a;
     memset(&a, 0, sizeof(a));
     a.C = C; a.D = D; a.Dp = (int)m.Dp;

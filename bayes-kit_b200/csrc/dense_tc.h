@@ -13,8 +13,10 @@ int dense_tc_prepare(Model& m, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t dense_tc_hmc_ws_bytes(const Model& m, int64_t C);
 int dense_tc_grad(const Model& m, const float* theta, int64_t C, float* grad, void* ws, size_t ws_bytes,
                   cudaStream_t st);
+// report_lp: the logp output is log p(theta) instead of the joint log density -- MALA(eps) is this
+// pipeline with L = 1 and step sqrt(2 eps) (mala.py:41-45 == one leapfrog step, test_equivalencies.py:12-32)
 int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* cache_valid, int64_t C,
                  double eps, int L, const float* metric, int64_t n_draws, const bk_rng* rng,
-                 const bk_draw_out& out, void* ws, size_t ws_bytes, cudaStream_t st);
+                 const bk_draw_out& out, void* ws, size_t ws_bytes, cudaStream_t st, bool report_lp = false);
 
 }  // namespace bk

@@ -298,8 +298,12 @@ int bk_iat_ess(const void* x, int32_t dtype, const bk_series_layout* layout, int
     BK_CHECK_ARG(estimator == BK_IAT_IPSE || estimator == BK_IAT_IMSE, "bk_iat_ess: bad estimator %d",
                  estimator);
     if (layout->n_series == 0) return BK_OK;
-    return acf_launch(view_of(x, dtype, layout), 1, estimator, nullptr, iat_out, ess_out,
-                      (cudaStream_t)stream);
+    // BK_ESS=block selects the block-per-series kernel (whole series staged in shared memory)
+    const char* e = getenv("BK_ESS");
+    if (e && e[0] == 'b')
+        return acf_launch(view_of(x, dtype, layout), 1, estimator, nullptr, iat_out, ess_out,
+                          (cudaStream_t)stream);
+    return ess_stream_launch(view_of(x, dtype, layout), estimator, iat_out, ess_out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

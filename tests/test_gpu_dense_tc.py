@@ -151,3 +151,27 @@ def test_logreg_tc_gradient_and_hmc(bk):
     assert (a != oa[0]).mean() <= 0.03
     same = a == oa[0]
     assert np.abs(np_(d)[0][same] - od[0][same]).max() <= 2e-2
+
+
+@pytest.mark.parametrize("D,C,eps", [(1000, 300, 2e-3), (200, 513, 1e-2), (128, 64, 5e-3)])
+def test_mala_tc_vs_oracle(bk, D, C, eps):
+    """MALA on the dense plugin (fp32) runs as begin -> split-precision tcgen05 gradient ->
+    accept (one leapfrog step of size sqrt(2 eps), test_equivalencies.py:12-32).  Against the
+    fp64 oracle's MALA (mala.py:40-66) under the same injected streams: identical accept
+    decisions away from ties, draws to fp32 rounding, log p(theta) to the split tolerance."""
+    rng = np.random.default_rng(D + 1)
+    P = DensePrecGauss.c2_precision(D, 0)
+    n = 3
+    th0 = rng.normal(size=(C, D)).astype(np.float32).astype(np.float64)
+    zs = rng.standard_normal((n, C, D)).astype(np.float32).astype(np.float64)
+    us = rng.random((n, C)).astype(np.float32).astype(np.float64)
+    od, ol, oa = osm.mala_batch(DensePrecGauss(P), th0, zs, us, eps)
+    s = bk.MALA(bk.DensePrecGauss(P, dtype=torch.float32), eps, init=th0)
+    d, l = s.sample_n(n, normals=zs, uniforms=us)
+    d, l, a = np_(d).astype(np.float64), np_(l).astype(np.float64), np_(s.last_accept).astype(bool)
+    same = np.ones(C, dtype=bool)
+    for t in range(n):
+        same &= a[t] == oa[t]                    # a chain is compared until its first flipped decision
+        assert same.mean() >= 0.97
+        assert np.abs(d[t][same] - od[t][same]).max() <= 2e-5 * (t + 1)
+        np.testing.assert_allclose(l[t][same], ol[t][same], rtol=2e-5, atol=2e-2)
