@@ -12,7 +12,9 @@ namespace bk {
 
 template <typename T>
 struct SmcArgs {
-    T* thetas;
+    T* thetas;                 // [M, D] moved particles (out)
+    const T* src;              // particles to move: row src_idx[m] (the pending resample) or row m
+    const int64_t* src_idx;    // [M] or NULL
     int64_t M;
     int D, vec;
     const T *mu, *pl, *m0, *p0;
@@ -38,44 +40,67 @@ __device__ __forceinline__ void gpl_terms(const T (&x)[4 * J], const T (&mu)[4 *
     pr = A::mul(T(-0.5), group_sum<G>(s2));
 }
 
+// Persistent groups: a group of G lanes owns elements 4*lane..4*lane+3 (per j) of EVERY particle it
+// visits, so the model's per-dimension parameters are loaded once and stay in registers.  The
+// resample index and the particle row of the NEXT visit are requested before the current particle is
+// processed (two dependent global loads deep), the accept uniform is drawn by the group's first lane only.
 template <typename T, int G, int J>
 __global__ void __launch_bounds__(128) k_smc_move_weight(SmcArgs<T> a) {
     using A = Ar<T>;
     constexpr int NE = 4 * J;
-    const int64_t raw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const bool active = raw < a.M;
-    const int64_t m = active ? raw : a.M - 1;
+    const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / G;
+    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int64_t n_it = (a.M + n_groups - 1) / n_groups;       // same trip count for every lane of a warp
     Lanes<T, G, J> ln;
     ln.lane = threadIdx.x % G;
     ln.D = a.D;
     ln.vec = a.vec != 0;
-    T mu[NE], pl[NE], m0[NE], p0[NE], th[NE], z[NE], st[NE];
+    T mu[NE], pl[NE], m0[NE], p0[NE];
     ln.load(a.mu, mu, T(0));
     ln.load(a.pl, pl, T(0));
     ln.load(a.m0, m0, T(0));
     ln.load(a.p0, p0, T(0));
-    ln.load(a.thetas + m * (int64_t)a.D, th, T(0));
-    ln.normals(a.rng, a.M, m, 0, z);
+    auto particle = [&](int64_t it) { const int64_t r = g0 + it * n_groups; return r < a.M ? r : a.M - 1; };
+    auto row_of = [&](int64_t m) { return a.src_idx ? a.src_idx[m] : m; };
+    T nx[NE];                                  // particle of the next visit
+    int64_t row_nn = 0;                        // resample index of the visit after that
+    if (n_it > 0) ln.load(a.src + row_of(particle(0)) * (int64_t)a.D, nx, T(0));
+    if (n_it > 1) row_nn = row_of(particle(1));
+    for (int64_t it = 0; it < n_it; ++it) {
+        const int64_t raw = g0 + it * n_groups;
+        const bool active = raw < a.M;
+        const int64_t m = active ? raw : a.M - 1;
+        T th[NE], z[NE], st[NE];
 #pragma unroll
-    for (int k = 0; k < NE; ++k) st[k] = A::add(th[k], A::mul(a.scale, z[k]));  // smc.py:81
-    T ll_c, pr_c, ll_s, pr_s;
-    gpl_terms<T, G, J>(th, mu, pl, m0, p0, ll_c, pr_c);
-    gpl_terms<T, G, J>(st, mu, pl, m0, p0, ll_s, pr_s);
-    const T lp_c = A::add(A::mul(ll_c, a.t0), pr_c), lp_s = A::add(A::mul(ll_s, a.t0), pr_s);
-    const bool acc = log_u(ln.uniform(a.rng, a.M, m, 0, 0)) < A::sub(lp_s, lp_c);  // smc.py:85
-    if (acc) {
+        for (int k = 0; k < NE; ++k) th[k] = nx[k];
+        // thetas[idxs] of the previous importance_resample (smc.py:75) is folded into this read
+        if (it + 1 < n_it) ln.load(a.src + row_nn * (int64_t)a.D, nx, T(0));
+        if (it + 2 < n_it) row_nn = row_of(particle(it + 2));
+        ln.normals(a.rng, a.M, m, 0, z);
 #pragma unroll
-        for (int k = 0; k < NE; ++k) th[k] = st[k];
-        ll_c = ll_s;
-        pr_c = pr_s;
-    }
-    // importance log-weight, both tempered densities in full (smc.py:67-70)
-    const T lw = A::sub(A::add(A::mul(ll_c, a.t1), pr_c), A::add(A::mul(ll_c, a.t0), pr_c));
-    if (active) {
-        ln.store(a.thetas + m * (int64_t)a.D, th);
-        if (ln.lane == 0) {
-            a.logw[m] = lw;
-            if (a.accept) a.accept[m] = acc ? 1 : 0;
+        for (int k = 0; k < NE; ++k) st[k] = A::add(th[k], A::mul(a.scale, z[k]));  // smc.py:81
+        T ll_c, pr_c, ll_s, pr_s;
+        gpl_terms<T, G, J>(th, mu, pl, m0, p0, ll_c, pr_c);
+        gpl_terms<T, G, J>(st, mu, pl, m0, p0, ll_s, pr_s);
+        const T lp_c = A::add(A::mul(ll_c, a.t0), pr_c), lp_s = A::add(A::mul(ll_s, a.t0), pr_s);
+        T lu = T(0);
+        if (ln.lane == 0) lu = log_u(ln.uniform(a.rng, a.M, m, 0, 0));
+        lu = __shfl_sync(0xffffffffu, lu, 0, G);
+        const bool acc = lu < A::sub(lp_s, lp_c);  // smc.py:85
+        if (acc) {
+#pragma unroll
+            for (int k = 0; k < NE; ++k) th[k] = st[k];
+            ll_c = ll_s;
+            pr_c = pr_s;
+        }
+        // importance log-weight, both tempered densities in full (smc.py:67-70)
+        const T lw = A::sub(A::add(A::mul(ll_c, a.t1), pr_c), A::add(A::mul(ll_c, a.t0), pr_c));
+        if (active) {
+            ln.store(a.thetas + m * (int64_t)a.D, th);
+            if (ln.lane == 0) {
+                a.logw[m] = lw;
+                if (a.accept) a.accept[m] = acc ? 1 : 0;
+            }
         }
     }
 }
@@ -83,18 +108,22 @@ __global__ void __launch_bounds__(128) k_smc_move_weight(SmcArgs<T> a) {
 template <typename T, int G, int J>
 static int launch_smc(const SmcArgs<T>& a, cudaStream_t st) {
     const int64_t per_block = 128 / G;
-    const int64_t blocks = (a.M + per_block - 1) / per_block;
-    k_smc_move_weight<T, G, J><<<(unsigned)blocks, 128, 0, st>>>(a);
+    const int64_t need = (a.M + per_block - 1) / per_block;
+    const int64_t cap = 148 * 8;                      // persistent: 8 CTAs of 128 threads per SM (62 registers)
+    k_smc_move_weight<T, G, J><<<(unsigned)(need < cap ? need : cap), 128, 0, st>>>(a);
     BK_LAUNCH_CHECK();
     return BK_OK;
 }
 
 template <typename T>
-static int smc_move_t(const Model& m, void* thetas, int64_t M, int n, int Tn, double scale,
-                      const bk_rng* rng, void* logw, int32_t* accept, cudaStream_t st) {
+static int smc_move_t(const Model& m, const void* src, const int64_t* src_idx, void* thetas, int64_t M,
+                      int n, int Tn, double scale, const bk_rng* rng, void* logw, int32_t* accept,
+                      cudaStream_t st) {
     SmcArgs<T> a;
     memset(&a, 0, sizeof(a));
     a.thetas = (T*)thetas;
+    a.src = (const T*)src;
+    a.src_idx = src_idx;
     a.M = M;
     a.D = (int)m.d.dims;
     a.mu = (const T*)m.d.mu; a.pl = (const T*)m.d.prec; a.m0 = (const T*)m.d.m0; a.p0 = (const T*)m.d.p0;
@@ -105,7 +134,7 @@ static int smc_move_t(const Model& m, void* thetas, int64_t M, int n, int Tn, do
     a.logw = (T*)logw;
     a.accept = accept;
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-    a.vec = (a.D % 4 == 0 && al(thetas) && al(a.mu) && al(a.pl) && al(a.m0) && al(a.p0) &&
+    a.vec = (a.D % 4 == 0 && al(thetas) && al(src) && al(a.mu) && al(a.pl) && al(a.m0) && al(a.p0) &&
              (rng->mode != BK_RNG_INJECTED || al(rng->normals))) ? 1 : 0;
     const int D = a.D;
     if (D <= 4) return launch_smc<T, 1, 1>(a, st);
@@ -323,18 +352,29 @@ extern "C" {
 
 int bk_smc_move_weight(uint64_t handle, void* thetas, int64_t M, int32_t n, int32_t T, double scale,
                        const bk_rng* rng, void* logw_out, int32_t* accept_out, void* stream) {
+    return bk_smc_gather_move_weight(handle, thetas, nullptr, thetas, M, n, T, scale, rng, logw_out,
+                                     accept_out, stream);
+}
+
+int bk_smc_gather_move_weight(uint64_t handle, const void* src, const int64_t* src_idx, void* thetas,
+                              int64_t M, int32_t n, int32_t T, double scale, const bk_rng* rng,
+                              void* logw_out, int32_t* accept_out, void* stream) {
     const Model* m = get_model(handle);
     if (!m) return BK_E_HANDLE;
     BK_CHECK_ARG(m->d.kind == BK_MODEL_GAUSS_PRIOR_LIK,
                  "bk_smc_move_weight: model must be GAUSS_PRIOR_LIK (log_prior/log_likelihood)");
-    BK_CHECK_ARG(thetas && logw_out && rng && M >= 0, "bk_smc_move_weight: bad argument");
+    BK_CHECK_ARG(src && thetas && logw_out && rng && M >= 0, "bk_smc_move_weight: bad argument");
+    BK_CHECK_ARG(!src_idx || src != thetas,
+                 "bk_smc_gather_move_weight: a gathered move cannot run in place (src == thetas)");
     BK_CHECK_ARG(T >= 1 && n >= 1 && n <= T, "bk_smc_move_weight: need 1 <= n <= T (n=%d, T=%d)", n, T);
     BK_CHECK_ARG(rng->mode != BK_RNG_INJECTED || (rng->normals && rng->uniforms && rng->n_uniform >= 1),
                  "bk_smc_move_weight: injected rng needs normals/uniforms");
     if (M == 0) return BK_OK;
     if (m->d.dtype == BK_F64)
-        return smc_move_t<double>(*m, thetas, M, n, T, scale, rng, logw_out, accept_out, (cudaStream_t)stream);
-    return smc_move_t<float>(*m, thetas, M, n, T, scale, rng, logw_out, accept_out, (cudaStream_t)stream);
+        return smc_move_t<double>(*m, src, src_idx, thetas, M, n, T, scale, rng, logw_out, accept_out,
+                                  (cudaStream_t)stream);
+    return smc_move_t<float>(*m, src, src_idx, thetas, M, n, T, scale, rng, logw_out, accept_out,
+                             (cudaStream_t)stream);
 }
 
 size_t bk_smc_resample_workspace_bytes(int64_t M) {

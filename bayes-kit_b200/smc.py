@@ -77,8 +77,9 @@ class TemperedLikelihoodSMC:
             th = sample_initial
             if th.shape[0] == self.M and self._world > 1:
                 th = th[self._lo:self._hi]
-        self.thetas = to_dev(th, self.dtype, self.device).clone()
-        self.D = self.thetas.shape[1]
+        self._thetas = to_dev(th, self.dtype, self.device).clone()
+        self._pending = None   # (all-gathered particles, resample indices) not yet materialised
+        self.D = self._thetas.shape[1]
         if self.D != self._model.dims():
             raise ValueError("sample_initial returned the wrong dimension")
         self._ws = Workspace(self.device)
@@ -87,6 +88,25 @@ class TemperedLikelihoodSMC:
         self._stats_log = []  # per temperature: device tensor [shift, sum w, sum w^2]
 
     # ---- reference surface -----------------------------------------------------------
+    @property
+    def thetas(self) -> torch.Tensor:
+        """Current particles [M_local, D] (smc.py:23,60).  The resampling gather
+        ``thetas[idxs]`` (smc.py:75) is normally folded into the next move's read;
+        it is materialised here when the particles are asked for."""
+        if self._pending is not None:
+            src, idx = self._pending
+            new = torch.empty(idx.shape[0], self.D, dtype=self.dtype, device=self.device)
+            with torch.cuda.device(self.device):
+                L.check(L.lib().bk_gather_rows(src.data_ptr(), idx.data_ptr(), idx.shape[0], self.D,
+                                               L.BK_F32 if self.dtype == torch.float32 else L.BK_F64,
+                                               new.data_ptr(), stream_ptr(self.device)))
+            self._thetas, self._pending = new, None
+        return self._thetas
+
+    @thetas.setter
+    def thetas(self, value) -> None:
+        self._thetas, self._pending = to_dev(value, self.dtype, self.device).clone(), None
+
     def log_prior(self, theta):
         return self._model.log_prior(theta)
 
@@ -118,7 +138,7 @@ class TemperedLikelihoodSMC:
         reference's recorded legacy-RNG streams (parity mode): proposal normals
         [M, D], accept uniforms [M], resampling uniforms [M] (systematic: [1])."""
         lib = L.lib()
-        Ml = self.thetas.shape[0]
+        Ml = self._hi - self._lo
         st = stream_ptr(self.device)
         logw = torch.empty(Ml, dtype=self.dtype, device=self.device)
         acc = torch.empty(Ml, dtype=torch.int32, device=self.device)
@@ -128,12 +148,20 @@ class TemperedLikelihoodSMC:
         rng = make_rng(self._seed, n, self._lo, normals, acc_uniforms, 1)
         mode = L.RESAMPLE_MULTINOMIAL if self.resample == "multinomial" else L.RESAMPLE_SYSTEMATIC
         with torch.cuda.device(self.device):
-            L.check(lib.bk_smc_move_weight(self._model.handle, self.thetas.data_ptr(), Ml, n, self.N,
-                                           self.kernel.scale, C.byref(rng), logw.data_ptr(),
-                                           acc.data_ptr(), st))
+            if self._pending is not None:     # move reads thetas_prev[idx]: gather + move in one pass
+                src, src_idx = self._pending
+                moved = torch.empty(Ml, self.D, dtype=self.dtype, device=self.device)
+                L.check(lib.bk_smc_gather_move_weight(
+                    self._model.handle, src.data_ptr(), src_idx.data_ptr(), moved.data_ptr(), Ml, n, self.N,
+                    self.kernel.scale, C.byref(rng), logw.data_ptr(), acc.data_ptr(), st))
+                self._thetas, self._pending = moved, None
+            else:
+                L.check(lib.bk_smc_move_weight(self._model.handle, self._thetas.data_ptr(), Ml, n, self.N,
+                                               self.kernel.scale, C.byref(rng), logw.data_ptr(),
+                                               acc.data_ptr(), st))
             # --- the naturally global step: normaliser + resampling ---------------------
             logw_all = D_.all_gather_cat(logw, self._group)      # [M]
-            thetas_all = D_.all_gather_cat(self.thetas, self._group)  # [M, D]
+            thetas_all = D_.all_gather_cat(self._thetas, self._group)  # [M, D]
             Mg = logw_all.shape[0]
             wp, wn = self._ws.get(lib.bk_smc_resample_workspace_bytes(Mg))
             stats = torch.empty(3, dtype=torch.float64, device=self.device)
@@ -151,10 +179,6 @@ class TemperedLikelihoodSMC:
             L.check(lib.bk_smc_resample_indices_dev(
                 logw_all.data_ptr(), Mg, L.BK_F32 if self.dtype == torch.float32 else L.BK_F64, mode,
                 stats.data_ptr(), ptr(ru), C.byref(rrng), Ml, self._lo, idx.data_ptr(), None, wp, wn, st))
-            new = torch.empty_like(self.thetas)
-            L.check(lib.bk_gather_rows(thetas_all.data_ptr(), idx.data_ptr(), Ml, self.D,
-                                       L.BK_F32 if self.dtype == torch.float32 else L.BK_F64,
-                                       new.data_ptr(), st))
-        self.thetas = new
+        self._pending = (thetas_all, idx)     # thetas[idxs]: folded into the next move (or .thetas)
         self.last_indices = idx
         self.last_accept = acc

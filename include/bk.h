@@ -183,6 +183,15 @@ BK_API int bk_drghmc_sample(uint64_t handle, void* theta, void* rho, int64_t C, 
 BK_API int bk_smc_move_weight(uint64_t handle, void* thetas, int64_t M, int32_t n, int32_t T,
                        double scale, const bk_rng* rng, void* logw_out, int32_t* accept_out,
                        void* stream);
+/* Same move with the previous temperature's resampling gather folded into the
+ * read: particle m starts from src[src_idx[m]] (src_idx NULL: src[m]) and the
+ * moved particle is written to thetas[m] -- thetas[idxs] (smc.py:75) followed by
+ * the kernel loop (smc.py:54-57) in one pass over HBM.  src [*, D] is the
+ * (all-gathered) particle array the indices refer to; src != thetas when
+ * src_idx is given. */
+BK_API int bk_smc_gather_move_weight(uint64_t handle, const void* src, const int64_t* src_idx,
+                       void* thetas, int64_t M, int32_t n, int32_t T, double scale,
+                       const bk_rng* rng, void* logw_out, int32_t* accept_out, void* stream);
 BK_API size_t bk_smc_resample_workspace_bytes(int64_t M);
 /* local reduction of the log-weights: stats_out[0] = max, [1] = sum exp(logw -
  * shift), [2] = sum exp(..)^2 where shift = max (SYSTEMATIC) or 0
