@@ -14,6 +14,8 @@
 //   k_hlr_finish: fixed-order sum over the observation slices (deterministic: no
 //     atomics) + the hierarchical prior terms.
 // The tcgen05 version of the two contractions is the next step for this plugin.
+#include <stdlib.h>
+
 #include "model.h"
 
 namespace bk {
@@ -163,9 +165,11 @@ __global__ void k_hlr_finish(const T* __restrict__ theta, const T* __restrict__ 
     sr = warp_sum(sr);
     ss = warp_sum(ss);
     if (lane == 0) {
-        T ll = T(0);
-        for (int s = 0; s < n_split; ++s) ll += part_ll[(int64_t)s * C + c];
-        lp[c] = ll - T(Dx) * lam - T(0.5) * e2 * ss - T(0.5) * mu * mu - T(0.5) * ep2 + lam;
+        if (lp) {
+            T ll = T(0);
+            for (int s = 0; s < n_split; ++s) ll += part_ll[(int64_t)s * C + c];
+            lp[c] = ll - T(Dx) * lam - T(0.5) * e2 * ss - T(0.5) * mu * mu - T(0.5) * ep2 + lam;
+        }
         if (grad) {
             grad[c * D + Dx] = e2 * sr - mu;
             grad[c * D + Dx + 1] = -T(Dx) + e2 * ss - ep2 + T(1);
@@ -200,12 +204,18 @@ static int hlr_eval_t(const Model& m, const T* theta, int64_t C, T* lp, T* grad,
     const int D = (int)m.d.dims, Dx = D - 2;
     const int64_t N = m.d.n_obs;
     if constexpr (sizeof(T) == 4) {
-        if (!precise && hlr_tc_enabled(m)) {   // interior leapfrog gradient: tcgen05, bf16 operands
+        // tcgen05 paths (logreg_tc.cu): leapfrog gradients with bf16 operands (precise = false),
+        // and the density on its own -- what a Metropolis test consumes -- with split-precision logits
+        if (hlr_tc_enabled(m) && (!precise || !grad)) {
             float *pg, *pl;
             int ns;
-            int rc = hlr_tc_partial(m, theta, C, ws, ws_bytes, &pg, &pl, &ns, st);
+            const char* dbg = getenv("BK_HLR_DEBUG");   // bit 2: time the gradient-only kernel through the public call
+            const bool no_ll = !lp || (dbg && (atoi(dbg) & 2));
+            const int mode = precise ? HLR_TC_LP : (no_ll ? HLR_TC_GRAD : HLR_TC_GRAD_LL);
+            int rc = hlr_tc_partial(m, theta, C, ws, ws_bytes, &pg, &pl, &ns, st, mode);
             if (rc) return rc;
-            k_hlr_finish<float><<<(unsigned)((C * 32 + 255) / 256), 256, 0, st>>>(theta, pg, pl, C, Dx, D, ns, lp, grad);
+            k_hlr_finish<float><<<(unsigned)((C * 32 + 255) / 256), 256, 0, st>>>(theta, pg, pl, C, Dx, D, ns, lp,
+                                                                                 precise ? nullptr : grad);
             BK_LAUNCH_CHECK();
             return BK_OK;
         }

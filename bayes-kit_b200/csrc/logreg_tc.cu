@@ -8,13 +8,21 @@
 //   epi    r[c, n]  = y_n - sigmoid(Z);  ll[c] += y_n Z - softplus(Z)   (registers; thread = chain)
 //          r -> bf16 -> shared memory as the K-major A operand of GEMM2
 //   GEMM2  G[c, j] += sum_n r[c, n] X[n, j]              (tcgen05, D2 persistent in TMEM)
-// X is streamed twice per tile by TMA (as [n][j] for GEMM1 and as the pre-transposed
-// [j][n] copy for GEMM2, both K-major / 128B swizzle, both L2-resident: 2 x 26 MB at
-// c3).  Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = epilogue
-// (lane quarter = warp % 4, observation half = (warp - 2) / 4).
-// Operands are bf16: like the dense plugin this path serves the INTERIOR leapfrog
-// gradients; the endpoint gradient / log density that enter the Metropolis test
-// come from the fp32 CUDA-core evaluator (logreg.cu).
+// X is streamed ONCE per tile by TMA ([n][j], 128B swizzle, L2-resident: 26 MB at c3)
+// through a 4-stage ring: the same shared-memory tile is GEMM1's K-major B operand
+// (N = n, K = j) and GEMM2's MN-major B operand (N = j, K = n) -- no transposed copy.
+// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = epilogue
+// (k_hlr_tc: 16 warps, lane quarter = warp % 4, observation part = (warp - 2) / 4).
+// Operands are bf16: like the dense plugin this kernel serves the leapfrog GRADIENTS
+// (any deterministic gradient function keeps the leapfrog map reversible and volume
+// preserving).  Without the log-likelihood the pointwise stage is ONE MUFU op per
+// logit (sigmoid = 0.5 + 0.5 tanh(z/2), tanh.approx) so it keeps pace with the two
+// 128x128x128 MMAs of a tile.
+//
+// The log density that enters the Metropolis test comes from k_hlr_lp_tc below: the
+// same tiling, logits from a 3-pass bf16 split (X_hi b_hi + X_hi b_lo + X_lo b_hi,
+// ~2^-16 relative, all three passes into one TMEM accumulator), pointwise
+// y z - softplus(z) in fp32 with per-tile sums carried in fp64, no second GEMM.
 #include <stdlib.h>
 
 #include "model.h"
@@ -27,12 +35,27 @@ using namespace ptx;
 namespace hlrtc {
 constexpr int CT = 128, NT = 128, KJ = 128;
 constexpr int ATOM = 128 * 64 * 2;                    // one [128 rows x 64 k] swizzle block = 16 KB
-constexpr int STAGE_BYTES = 4 * ATOM + 1024;          // X (2 atoms) + X^T (2 atoms) + y tile
-constexpr int OFF_A1 = 0, OFF_STAGE = 2 * ATOM, OFF_A2 = OFF_STAGE + 2 * STAGE_BYTES;
-constexpr int OFF_BARS = OFF_A2 + 2 * ATOM, OFF_LL = OFF_BARS + 256;
-constexpr int SMEM_BYTES = OFF_LL + 2 * CT * 4 + 1024;
-constexpr int THREADS = 320;
+constexpr int NSTAGE = 3;
+constexpr int STAGE_BYTES = 2 * ATOM + 1024;          // X tile (2 atoms) + y tile
+constexpr int OFF_A1 = 0, OFF_STAGE = 2 * ATOM, OFF_A2 = OFF_STAGE + NSTAGE * STAGE_BYTES;
+constexpr int OFF_BARS = OFF_A2 + 4 * ATOM, OFF_LL = OFF_BARS + 256;   // R is double-buffered
+constexpr int THREADS = 320;                          // k_hlr_lp_tc: 8 epilogue warps
+constexpr int EWARPS = 16, EPARTS = EWARPS / 4;       // k_hlr_tc: 16 epilogue warps (4 observation parts)
+constexpr int GTHREADS = 64 + 32 * EWARPS;
+constexpr int SMEM_BYTES = OFF_LL + EPARTS * CT * 4 + 1024;
 constexpr uint32_t IDESC = idesc_bf16(128, 128);
+constexpr uint32_t IDESC_BMN = IDESC | (1u << 16);     // B operand MN-major (bit 16 = b_major)
+// MN-major SWIZZLE_128B operand: 64 MN-elements (128 B) contiguous, 8 K-rows 128 B apart form one
+// 1024-byte swizzle atom; LBO = byte distance between 64-element MN blocks, SBO = between 8-row K groups
+__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 
 struct Args {
     int64_t C, N;
@@ -41,22 +64,34 @@ struct Args {
     const float* y;             // [Np] zero padded
     float* part_g;              // [n_split, C, Dx]
     float* part_ll;             // [n_split, C]
+    int need_ll;                // 0: gradient only (one MUFU op per logit)
+    float g_scale;              // 1 (gradient needs no rescaling; kept for experiments)
+    int debug;                  // BK_HLR_DEBUG bits (timing experiments): 1 = skip the pointwise math
 };
 
-__global__ void __launch_bounds__(THREADS, 1)
-k_hlr_tc(const __grid_constant__ CUtensorMap mapBeta, const __grid_constant__ CUtensorMap mapX,
-         const __grid_constant__ CUtensorMap mapXT, const Args a) {
+__device__ __forceinline__ float tanh_approx(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+    return t;
+}
+
+template <bool NEED_LL>   // compile-time: a per-logit branch would serialise the MUFU latencies
+__global__ void __launch_bounds__(GTHREADS, 1)
+k_hlr_tc(const __grid_constant__ CUtensorMap mapBeta, const __grid_constant__ CUtensorMap mapX, const Args a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t sA1 = base + OFF_A1, sA2 = base + OFF_A2, bars = base + OFF_BARS;
     auto stage = [&](int s) { return base + OFF_STAGE + (uint32_t)s * STAGE_BYTES; };
     auto full = [&](int s) { return bars + 8u * s; };
-    auto empty = [&](int s) { return bars + 8u * (2 + s); };
-    auto d1_full = [&](int b) { return bars + 8u * (4 + b); };
-    const uint32_t a2_full = bars + 8u * 6, a2_free = bars + 8u * 7, d2_full = bars + 8u * 8,
-                   beta_full = bars + 8u * 9, tmem_slot = bars + 8u * 10;
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + OFF_BARS + 80);
+    auto empty = [&](int s) { return bars + 8u * (NSTAGE + s); };
+    auto d1_full = [&](int b) { return bars + 8u * (2 * NSTAGE + b); };
+    auto a2_full = [&](int b) { return bars + 8u * (2 * NSTAGE + 2 + b); };
+    auto a2_free = [&](int b) { return bars + 8u * (2 * NSTAGE + 4 + b); };
+    const uint32_t d2_full = bars + 8u * (2 * NSTAGE + 6), beta_full = bars + 8u * (2 * NSTAGE + 7),
+                   tmem_slot = bars + 8u * (2 * NSTAGE + 8);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(gbase + OFF_BARS + 8 * (2 * NSTAGE + 8));
     float* lls = reinterpret_cast<float*>(gbase + OFF_LL);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -67,8 +102,9 @@ k_hlr_tc(const __grid_constant__ CUtensorMap mapBeta, const __grid_constant__ CU
     const int T = n_end > n_begin ? (int)((n_end - n_begin + NT - 1) / NT) : 0;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); mbar_init(d1_full(s), 1); }
-        mbar_init(a2_full, 256); mbar_init(a2_free, 1); mbar_init(d2_full, 1); mbar_init(beta_full, 1);
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(d1_full(s), 1); mbar_init(a2_full(s), 16 * EWARPS); mbar_init(a2_free(s), 1); }
+        mbar_init(d2_full, 1); mbar_init(beta_full, 1);
         mbar_init_fence();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -84,36 +120,35 @@ k_hlr_tc(const __grid_constant__ CUtensorMap mapBeta, const __grid_constant__ CU
             tma_load_2d(sA1, &mapBeta, beta_full, 0, (int)c0);
             tma_load_2d(sA1 + ATOM, &mapBeta, beta_full, 64, (int)c0);
             for (int i = 0; i < T; ++i) {
-                const int s = i & 1;
-                const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+                const int s = i % NSTAGE;
+                const uint32_t ph = (uint32_t)(i / NSTAGE) & 1u;
                 const int n0 = (int)(n_begin + (int64_t)i * NT);
                 mbar_wait(empty(s), ph ^ 1u);
-                mbar_expect_tx(full(s), 4 * ATOM + NT * 4);
+                mbar_expect_tx(full(s), 2 * ATOM + NT * 4);
                 const uint32_t st = stage(s);
                 tma_load_2d(st, &mapX, full(s), 0, n0);                 // X[n0.., j 0..63]
                 tma_load_2d(st + ATOM, &mapX, full(s), 64, n0);         // X[n0.., j 64..127]
-                tma_load_2d(st + 2 * ATOM, &mapXT, full(s), n0, 0);     // X^T[j, n0..n0+63]
-                tma_load_2d(st + 3 * ATOM, &mapXT, full(s), n0 + 64, 0);
-                bulk_load(st + 4 * ATOM, a.y + n0, NT * 4, full(s));
+                bulk_load(st + 2 * ATOM, a.y + n0, NT * 4, full(s));
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && T > 0) {
             auto kdesc = [](uint32_t tile, int kk) { return umma_desc<128>(tile + (kk >> 2) * ATOM + (kk & 3) * 32); };
-            auto mma2 = [&](int t) {   // G += R_t . X_t   (A = R in smem, B = X^T tile)
-                const int s = t & 1;
-                mbar_wait(a2_full, (uint32_t)t & 1u);
+            auto mma2 = [&](int t) {   // G += R_t . X_t   (A = R in smem, B = the X tile read MN-major)
+                const int s = t % NSTAGE, b = t & 1;
+                mbar_wait(a2_full(b), (uint32_t)(t >> 1) & 1u);
                 tc_fence_after();
-                const uint32_t xt = stage(s) + 2 * ATOM;
+                const uint32_t xt = stage(s), ra = sA2 + (uint32_t)b * 2 * ATOM;
 #pragma unroll
-                for (int kk = 0; kk < NT / 16; ++kk) umma(tD2, kdesc(sA2, kk), kdesc(xt, kk), IDESC, (t | kk) != 0);
-                umma_commit(empty(s));     // stage reusable once GEMM2 has read X^T
-                umma_commit(a2_free);      // R buffer reusable
+                for (int kk = 0; kk < NT / 16; ++kk)   // 16 observations = two 8-row swizzle atoms = 2048 B
+                    umma(tD2, kdesc(ra, kk), umma_desc_mn128(xt + kk * 2048, ATOM, 1024), IDESC_BMN, (t | kk) != 0);
+                umma_commit(empty(s));     // stage reusable once GEMM2 has read the tile
+                umma_commit(a2_free(b));   // R buffer reusable
             };
             mbar_wait(beta_full, 0);
             for (int i = 0; i < T; ++i) {
-                const int s = i & 1;
-                mbar_wait(full(s), (uint32_t)(i >> 1) & 1u);
+                const int s = i % NSTAGE;
+                mbar_wait(full(s), (uint32_t)(i / NSTAGE) & 1u);
                 tc_fence_after();
                 const uint32_t d1 = tD1 + (uint32_t)(i & 1) * 128;
 #pragma unroll
@@ -125,55 +160,78 @@ k_hlr_tc(const __grid_constant__ CUtensorMap mapBeta, const __grid_constant__ CU
             umma_commit(d2_full);
         }
     } else {
-        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        // 16 epilogue warps = two groups of 8 that take alternate tiles (group g owns D1 buffer g and R
+        // buffer g), so the fixed latencies of a tile's hand-offs (TMEM load, proxy fence, mbarrier round
+        // trips) overlap with the other group's tile.  TMEM lane quarter = warp % 4 (hardware rule),
+        // observation half = bit 2 of (warp - 2).
+        const int quarter = warp & 3, grp = (warp - 2) >> 3, part = ((warp - 2) >> 2) & 1;
+        const int part4 = grp * 2 + part;                      // 0..3: slice of the final gradient read
+        constexpr int PW = NT / 2;                             // observations per thread per tile (64)
         const int cl = quarter * 32 + lane;                    // chain within the tile = TMEM lane
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+        // this chain's row of R: PW k's = PW/8 16-byte chunks, inside atom (part * PW) / 64
+        const uint32_t rrow0 = sA2 + (uint32_t)((part * PW) >> 6) * ATOM + (uint32_t)(cl >> 3) * 1024 +
+                               (uint32_t)(cl & 7) * 128;
+        const int kc0 = ((part * PW) & 63) >> 3;
         float ll = 0.f;
-        for (int i = 0; i < T; ++i) {
+        for (int i = grp; i < T; i += 2) {
             const int64_t n0 = n_begin + (int64_t)i * NT;
-            mbar_wait(full(i & 1), (uint32_t)(i >> 1) & 1u);   // acquire the TMA-written y tile
+            mbar_wait(full(i % NSTAGE), (uint32_t)(i / NSTAGE) & 1u);   // acquire the TMA-written y tile
             mbar_wait(d1_full(i & 1), (uint32_t)(i >> 1) & 1u);
             tc_fence_after();
-            const float* ys = reinterpret_cast<const float*>(gbase + OFF_STAGE + (i & 1) * STAGE_BYTES + 4 * ATOM);
-            const uint32_t d1 = tD1 + (uint32_t)(i & 1) * 128 + lane_sel + (uint32_t)(half * 64);
-            const uint32_t rrow = sA2 + (uint32_t)half * ATOM + (uint32_t)(cl >> 3) * 1024 + (uint32_t)(cl & 7) * 128;
-            uint32_t packed[32];     // this chain's 64 residuals of the tile, bf16x2
+            const float* ys = reinterpret_cast<const float*>(gbase + OFF_STAGE + (i % NSTAGE) * STAGE_BYTES +
+                                                             2 * ATOM) + part * PW;
+            const uint32_t d1 = tD1 + (uint32_t)(i & 1) * 128 + lane_sel + (uint32_t)(part * PW);
+            uint32_t packed[PW / 2];     // this chain's residuals of the tile, bf16x2
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
+            for (int ch = 0; ch < PW / 16; ++ch) {
                 uint32_t zv[16];
                 tmem_ld16(d1 + ch * 16, zv);
+                if (a.debug & 1) {
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    float rr[2];
+                    for (int j = 0; j < 8; ++j) packed[ch * 8 + j] = zv[2 * j] & 0x3f803f80u;
+                    continue;
+                }
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int nl = half * 64 + ch * 16 + j + u;
-                        const float z = __uint_as_float(zv[j + u]);
-                        const float yv = ys[nl];
-                        const float e = __expf(-fabsf(z));                 // shared by sigmoid and softplus
-                        const float inv = __fdividef(1.0f, 1.0f + e);
-                        const float sig = z >= 0.f ? inv : e * inv;
-                        const bool live = n0 + nl < n_end;
-                        if (live) ll += yv * z - (fmaxf(z, 0.f) + __logf(1.0f + e));
-                        rr[u] = live ? yv - sig : 0.f;
+                for (int j4 = 0; j4 < 16; j4 += 4) {
+                    const float4 y4 = *reinterpret_cast<const float4*>(ys + ch * 16 + j4);   // broadcast
+                    const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+                    float rr[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float z = __uint_as_float(zv[j4 + u]);
+                        if constexpr (NEED_LL) {
+                            const bool live = n0 + part * PW + ch * 16 + j4 + u < n_end;
+                            const float e = __expf(-fabsf(z));             // shared by sigmoid and softplus
+                            const float inv = __fdividef(1.0f, 1.0f + e);
+                            const float sig = z >= 0.f ? inv : e * inv;
+                            if (live) ll += yv[u] * z - (fmaxf(z, 0.f) + __logf(1.0f + e));
+                            rr[u] = live ? yv[u] - sig : 0.f;
+                        } else {
+                            // z holds X.beta / 2 and ys holds y - 1/2 (0 on padded rows, where z = 0 too):
+                            // y - sigmoid(2z) = (y - 1/2) - tanh(z)/2 -- one MUFU op and one FMA per logit
+                            rr[u] = fmaf(-0.5f, tanh_approx(z), yv[u]);
+                        }
                     }
-                    __nv_bfloat162 p2 = __floats2bfloat162_rn(rr[0], rr[1]);
-                    packed[ch * 8 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&p2);
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn(rr[0], rr[1]), p1 = __floats2bfloat162_rn(rr[2], rr[3]);
+                    packed[ch * 8 + (j4 >> 1)] = *reinterpret_cast<uint32_t*>(&p0);
+                    packed[ch * 8 + (j4 >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
                 }
             }
-            // the math above overlapped GEMM2 of tile i-1; only now does R have to be free
-            mbar_wait(a2_free, (uint32_t)(i + 1) & 1u);
-            // 64 k's = eight 16-byte chunks of this chain's row, XOR-swizzled like the TMA would
+            // R is double-buffered: this buffer was last read by GEMM2 of tile i-2
+            mbar_wait(a2_free(i & 1), ((uint32_t)(i >> 1) + 1u) & 1u);
+            const uint32_t rrow = rrow0 + (uint32_t)(i & 1) * 2 * ATOM;
+            // 16-byte chunks of this chain's row, XOR-swizzled like the TMA would
 #pragma unroll
-            for (int kc = 0; kc < 8; ++kc) {
-                const uint32_t addr = rrow + (((uint32_t)kc ^ (uint32_t)(cl & 7)) << 4);
+            for (int kc = 0; kc < PW / 8; ++kc) {
+                const uint32_t addr = rrow + (((uint32_t)(kc0 + kc) ^ (uint32_t)(cl & 7)) << 4);
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[4 * kc]),
                              "r"(packed[4 * kc + 1]), "r"(packed[4 * kc + 2]), "r"(packed[4 * kc + 3])
                              : "memory");
             }
             fence_proxy_async_smem();
             tc_fence_before();
-            mbar_arrive(a2_full);
+            mbar_arrive(a2_full(i & 1));
         }
         // partial gradient of this slice: D2[c, j]
         const int64_t c = c0 + cl;
@@ -181,24 +239,31 @@ k_hlr_tc(const __grid_constant__ CUtensorMap mapBeta, const __grid_constant__ CU
             mbar_wait(d2_full, 0);
             tc_fence_after();
 #pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
+            for (int ch = 0; ch < 2; ++ch) {
                 uint32_t gv[16];
-                tmem_ld16(tD2 + lane_sel + (uint32_t)(half * 64 + ch * 16), gv);
+                tmem_ld16(tD2 + lane_sel + (uint32_t)(part4 * 32 + ch * 16), gv);
                 if (c < a.C) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const int jj = half * 64 + ch * 16 + j;
-                        if (jj < a.Dx) a.part_g[((int64_t)split * a.C + c) * a.Dx + jj] = __uint_as_float(gv[j]);
+                        const int jj = part4 * 32 + ch * 16 + j;
+                        if (jj < a.Dx) a.part_g[((int64_t)split * a.C + c) * a.Dx + jj] = __uint_as_float(gv[j]) * a.g_scale;
                     }
                 }
             }
         } else if (c < a.C) {
-            for (int jj = half * 64; jj < half * 64 + 64; ++jj)
+            for (int jj = part4 * 32; jj < part4 * 32 + 32; ++jj)
                 if (jj < a.Dx) a.part_g[((int64_t)split * a.C + c) * a.Dx + jj] = 0.f;
         }
-        lls[half * CT + cl] = ll;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (half == 0 && c < a.C) a.part_ll[(int64_t)split * a.C + c] = lls[cl] + lls[CT + cl];
+        if constexpr (NEED_LL) {
+            lls[part4 * CT + cl] = ll;
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EWARPS) : "memory");
+            if (part4 == 0 && c < a.C) {
+                float t = 0.f;
+#pragma unroll
+                for (int q = 0; q < EPARTS; ++q) t += lls[q * CT + cl];
+                a.part_ll[(int64_t)split * a.C + c] = t;
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -208,11 +273,135 @@ k_hlr_tc(const __grid_constant__ CUtensorMap mapBeta, const __grid_constant__ CU
     }
 }
 
+// ---- split-precision log-likelihood (the density that enters the Metropolis test) --------
+constexpr int LP_STAGE_BYTES = 4 * ATOM + 1024;       // X_hi (2 atoms) + X_lo (2 atoms) + y tile
+constexpr int LP_OFF_STAGE = 4 * ATOM;                // after beta_hi, beta_lo
+constexpr int LP_OFF_BARS = LP_OFF_STAGE + 2 * LP_STAGE_BYTES;
+constexpr int LP_OFF_LL = LP_OFF_BARS + 256;
+constexpr int LP_SMEM_BYTES = LP_OFF_LL + 2 * CT * 8 + 1024;
+
+__global__ void __launch_bounds__(THREADS, 1)
+k_hlr_lp_tc(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
+            const __grid_constant__ CUtensorMap mapXhi, const __grid_constant__ CUtensorMap mapXlo, const Args a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sBhi = base, sBlo = base + 2 * ATOM, bars = base + LP_OFF_BARS;
+    auto stage = [&](int s) { return base + LP_OFF_STAGE + (uint32_t)s * LP_STAGE_BYTES; };
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto slot_free = [&](int s) { return bars + 8u * (2 + s); };   // epilogue drained stage s AND accumulator s
+    auto d1_full = [&](int b) { return bars + 8u * (4 + b); };
+    const uint32_t beta_full = bars + 8u * 6, tmem_slot = bars + 8u * 7;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + LP_OFF_BARS + 56);
+    double* lls = reinterpret_cast<double*>(gbase + LP_OFF_LL);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t c0 = (int64_t)blockIdx.x * CT;
+    const int split = blockIdx.y;
+    const int64_t n_begin = split * a.rows_per_split;
+    const int64_t n_end = n_begin + a.rows_per_split < a.N ? n_begin + a.rows_per_split : a.N;
+    const int T = n_end > n_begin ? (int)((n_end - n_begin + NT - 1) / NT) : 0;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < 2; ++s) { mbar_init(full(s), 1); mbar_init(slot_free(s), 256); mbar_init(d1_full(s), 1); }
+        mbar_init(beta_full, 1);
+        mbar_init_fence();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(beta_full, 4 * ATOM);
+            tma_load_2d(sBhi, &mapBhi, beta_full, 0, (int)c0);
+            tma_load_2d(sBhi + ATOM, &mapBhi, beta_full, 64, (int)c0);
+            tma_load_2d(sBlo, &mapBlo, beta_full, 0, (int)c0);
+            tma_load_2d(sBlo + ATOM, &mapBlo, beta_full, 64, (int)c0);
+            for (int i = 0; i < T; ++i) {
+                const int s = i & 1;
+                const int n0 = (int)(n_begin + (int64_t)i * NT);
+                mbar_wait(slot_free(s), ((uint32_t)(i >> 1) & 1u) ^ 1u);
+                mbar_expect_tx(full(s), 4 * ATOM + NT * 4);
+                const uint32_t st = stage(s);
+                tma_load_2d(st, &mapXhi, full(s), 0, n0);
+                tma_load_2d(st + ATOM, &mapXhi, full(s), 64, n0);
+                tma_load_2d(st + 2 * ATOM, &mapXlo, full(s), 0, n0);
+                tma_load_2d(st + 3 * ATOM, &mapXlo, full(s), 64, n0);
+                bulk_load(st + 4 * ATOM, a.y + n0, NT * 4, full(s));
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && T > 0) {
+            auto kdesc = [](uint32_t tile, int kk) { return umma_desc<128>(tile + (kk >> 2) * ATOM + (kk & 3) * 32); };
+            mbar_wait(beta_full, 0);
+            for (int i = 0; i < T; ++i) {
+                const int s = i & 1;
+                mbar_wait(full(s), (uint32_t)(i >> 1) & 1u);    // implies slot_free(s): the producer waited for it
+                tc_fence_after();
+                const uint32_t d1 = tmem + (uint32_t)s * 128;
+                const uint32_t xhi = stage(s), xlo = stage(s) + 2 * ATOM;
+                // Z = b_hi X_hi + b_lo X_hi + b_hi X_lo, one accumulator
+#pragma unroll
+                for (int kk = 0; kk < KJ / 16; ++kk) umma(d1, kdesc(sBhi, kk), kdesc(xhi, kk), IDESC, kk != 0);
+#pragma unroll
+                for (int kk = 0; kk < KJ / 16; ++kk) umma(d1, kdesc(sBlo, kk), kdesc(xhi, kk), IDESC, 1u);
+#pragma unroll
+                for (int kk = 0; kk < KJ / 16; ++kk) umma(d1, kdesc(sBhi, kk), kdesc(xlo, kk), IDESC, 1u);
+                umma_commit(d1_full(s));
+            }
+        }
+    } else {
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        const int cl = quarter * 32 + lane;
+        const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+        double ll = 0.0;
+        for (int i = 0; i < T; ++i) {
+            const int s = i & 1;
+            const int64_t n0 = n_begin + (int64_t)i * NT;
+            mbar_wait(full(s), (uint32_t)(i >> 1) & 1u);       // acquire the TMA-written y tile
+            mbar_wait(d1_full(s), (uint32_t)(i >> 1) & 1u);
+            tc_fence_after();
+            const float* ys = reinterpret_cast<const float*>(gbase + LP_OFF_STAGE + s * LP_STAGE_BYTES + 4 * ATOM);
+            const uint32_t d1 = tmem + (uint32_t)s * 128 + lane_sel + (uint32_t)(half * 64);
+            float lt = 0.f;                                     // this tile: 64 terms in fp32
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t zv[16];
+                tmem_ld16(d1 + ch * 16, zv);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int nl = half * 64 + ch * 16 + j;
+                    const float z = __uint_as_float(zv[j]);
+                    const float e = __expf(-fabsf(z));
+                    const float t = ys[nl] * z - (fmaxf(z, 0.f) + __logf(1.0f + e));
+                    lt += (n0 + nl < n_end) ? t : 0.f;
+                }
+            }
+            ll += (double)lt;
+            tc_fence_before();
+            mbar_arrive(slot_free(s));                          // stage s and accumulator s may be refilled
+        }
+        lls[half * CT + cl] = ll;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int64_t c = c0 + cl;
+        if (half == 0 && c < a.C) a.part_ll[(int64_t)split * a.C + c] = (float)(lls[cl] + lls[CT + cl]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 256);
+    }
+}
+
 // ---- operand preparation ------------------------------------------------------------
-// X [N, Dx] fp32 -> Xb [Np, 128] bf16, XbT [128, Np] bf16, yp [Np] fp32 (zero padded)
+// X [N, Dx] fp32 -> Xb [Np, 128] bf16 (+ the residual Xlo), yp [Np] fp32 (zero padded)
 __global__ void k_hlr_prep_x(const float* __restrict__ X, const float* __restrict__ y, int64_t N, int64_t Np, int Dx,
-                             __nv_bfloat16* __restrict__ Xb, __nv_bfloat16* __restrict__ XbT,
-                             float* __restrict__ yp) {
+                             __nv_bfloat16* __restrict__ Xb, __nv_bfloat16* __restrict__ Xlo,
+                             float* __restrict__ yp, float* __restrict__ yh) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Np * KJ) return;
     const int64_t n = i / KJ;
@@ -220,17 +409,24 @@ __global__ void k_hlr_prep_x(const float* __restrict__ X, const float* __restric
     const float v = (n < N && j < Dx) ? X[n * Dx + j] : 0.f;
     const __nv_bfloat16 b = __float2bfloat16_rn(v);
     Xb[i] = b;
-    XbT[(int64_t)j * Np + n] = b;
-    if (j == 0) yp[n] = n < N ? y[n] : 0.f;
+    Xlo[i] = __float2bfloat16_rn(v - __bfloat162float(b));
+    if (j == 0) {
+        yp[n] = n < N ? y[n] : 0.f;
+        yh[n] = n < N ? y[n] - 0.5f : 0.f;   // y - 1/2; 0 on padded rows so their residual is exactly 0
+    }
 }
 // theta [C, D] fp32 -> beta_b [Cp, 128] bf16 (regressor columns only, zero padded)
 __global__ void k_hlr_prep_beta(const float* __restrict__ theta, int64_t C, int64_t Cp, int Dx, int D,
-                                __nv_bfloat16* __restrict__ out) {
+                                float scale, __nv_bfloat16* __restrict__ out,
+                                __nv_bfloat16* __restrict__ out_lo) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Cp * KJ) return;
     const int64_t c = i / KJ;
     const int j = (int)(i % KJ);
-    out[i] = __float2bfloat16_rn((c < C && j < Dx) ? theta[c * D + j] : 0.f);
+    const float v = (c < C && j < Dx) ? scale * theta[c * D + j] : 0.f;
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    out[i] = b;
+    if (out_lo) out_lo[i] = __float2bfloat16_rn(v - __bfloat162float(b));
 }
 
 }  // namespace hlrtc
@@ -242,7 +438,7 @@ static int64_t pad128(int64_t x) { return (x + 127) / 128 * 128; }
 size_t hlr_tc_model_ws_bytes(const bk_model_desc& d) {
     if (d.kind != BK_MODEL_HIER_LOGREG || d.dtype != BK_F32 || d.dims - 2 > KJ) return 0;
     const size_t Np = (size_t)pad128(d.n_obs);
-    return 2 * align_up(Np * KJ * 2, 256) + align_up(Np * 4, 256) + 1024;
+    return 2 * align_up(Np * KJ * 2, 256) + 2 * align_up(Np * 4, 256) + 1024;
 }
 
 int hlr_tc_prepare(Model& m, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -250,16 +446,17 @@ int hlr_tc_prepare(Model& m, void* ws, size_t ws_bytes, cudaStream_t st) {
     const int64_t Np = pad128(m.d.n_obs);
     Arena ar(ws, ws_bytes);
     m.Xb = ar.take<__nv_bfloat16>((size_t)Np * KJ);
-    m.XbT = ar.take<__nv_bfloat16>((size_t)Np * KJ);
+    m.Xlo = ar.take<__nv_bfloat16>((size_t)Np * KJ);
     m.yp = ar.take<float>((size_t)Np);
+    m.yh = ar.take<float>((size_t)Np);
     if (!ar.ok()) {
-        m.Xb = m.XbT = nullptr; m.yp = nullptr;
+        m.Xb = m.Xlo = nullptr; m.yp = m.yh = nullptr;
         set_error("bk_model_create: workspace too small for the tensor-core operands");
         return BK_E_WORKSPACE;
     }
     const int64_t n = Np * KJ;
     k_hlr_prep_x<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float*)m.d.X, (const float*)m.d.y, m.d.n_obs, Np,
-                                                              (int)m.d.dims - 2, m.Xb, m.XbT, m.yp);
+                                                              (int)m.d.dims - 2, m.Xb, m.Xlo, m.yp, m.yh);
     BK_LAUNCH_CHECK();
     return BK_OK;
 }
@@ -281,40 +478,55 @@ int hlr_tc_splits(int64_t C, int64_t N) {
 size_t hlr_tc_eval_ws_bytes(const Model& m, int64_t C) {
     const int Dx = (int)m.d.dims - 2;
     const int ns = hlr_tc_splits(C, m.d.n_obs);
-    return align_up((size_t)pad128(C) * KJ * 2, 256) + align_up((size_t)ns * C * Dx * 4, 256) +
+    return 2 * align_up((size_t)pad128(C) * KJ * 2, 256) + align_up((size_t)ns * C * Dx * 4, 256) +
            align_up((size_t)ns * C * 4, 256) + 1024;
 }
 
 // partial gradients / log-likelihoods of every observation slice -> part_g, part_ll
+// mode: HLR_TC_GRAD (gradient partials only), HLR_TC_GRAD_LL (+ bf16-grade log-likelihood),
+//       HLR_TC_LP (split-precision log-likelihood only, part_g untouched)
 int hlr_tc_partial(const Model& m, const float* theta, int64_t C, void* ws, size_t ws_bytes, float** part_g,
-                   float** part_ll, int* n_split, cudaStream_t st) {
+                   float** part_ll, int* n_split, cudaStream_t st, int mode) {
     const int D = (int)m.d.dims, Dx = D - 2;
     const int64_t N = m.d.n_obs, Np = pad128(N), Cp = pad128(C);
     const int ns = hlr_tc_splits(C, N);
     Arena ar(ws, ws_bytes);
     __nv_bfloat16* bb = ar.take<__nv_bfloat16>((size_t)Cp * KJ);
+    __nv_bfloat16* bl = ar.take<__nv_bfloat16>((size_t)Cp * KJ);
     float* pg = ar.take<float>((size_t)ns * C * Dx);
     float* pl = ar.take<float>((size_t)ns * C);
     if (!ar.ok()) { set_error("model eval workspace too small (%zu < %zu)", ws_bytes, ar.off); return BK_E_WORKSPACE; }
-    k_hlr_prep_beta<<<(unsigned)((Cp * KJ + 255) / 256), 256, 0, st>>>(theta, C, Cp, Dx, D, bb);
+    // gradient-only mode folds the 1/2 of sigmoid(z) = 1/2 + tanh(z/2)/2 into the operand (exact in bf16)
+    k_hlr_prep_beta<<<(unsigned)((Cp * KJ + 255) / 256), 256, 0, st>>>(theta, C, Cp, Dx, D,
+                                                                       mode == HLR_TC_GRAD ? 0.5f : 1.0f, bb,
+                                                                       mode == HLR_TC_LP ? bl : nullptr);
     BK_LAUNCH_CHECK();
-    CUtensorMap mB, mX, mXT;
+    CUtensorMap mB, mBl, mX, mXl;
     int rc;
     if ((rc = make_map_bf16(&mB, bb, Cp, KJ, KJ, CT))) return rc;
+    if ((rc = make_map_bf16(&mBl, bl, Cp, KJ, KJ, CT))) return rc;
     if ((rc = make_map_bf16(&mX, m.Xb, Np, KJ, KJ, NT))) return rc;
-    if ((rc = make_map_bf16(&mXT, m.XbT, KJ, Np, Np, KJ))) return rc;
+    if ((rc = make_map_bf16(&mXl, m.Xlo, Np, KJ, KJ, NT))) return rc;
     static bool attr = false;
     if (!attr) {
-        BK_CUDA(cudaFuncSetAttribute(k_hlr_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        BK_CUDA(cudaFuncSetAttribute(k_hlr_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        BK_CUDA(cudaFuncSetAttribute(k_hlr_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        BK_CUDA(cudaFuncSetAttribute(k_hlr_lp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, LP_SMEM_BYTES));
         attr = true;
     }
     Args a;
-    a.C = C; a.N = N; a.Dx = Dx; a.y = m.yp; a.part_g = pg; a.part_ll = pl;
+    a.C = C; a.N = N; a.Dx = Dx; a.part_g = pg; a.part_ll = pl;
+    a.y = mode == HLR_TC_GRAD ? m.yh : m.yp;
+    a.need_ll = mode == HLR_TC_GRAD_LL ? 1 : 0;
+    a.g_scale = 1.0f;
+    { const char* e = getenv("BK_HLR_DEBUG"); a.debug = e ? atoi(e) : 0; }
     int64_t rows = (N + ns - 1) / ns;
     a.rows_per_split = (rows + NT - 1) / NT * NT;
     dim3 grid((unsigned)(Cp / CT), (unsigned)ns);
     prof_begin(BK_PROF_GRAD, st);
-    k_hlr_tc<<<grid, THREADS, SMEM_BYTES, st>>>(mB, mX, mXT, a);
+    if (mode == HLR_TC_LP) k_hlr_lp_tc<<<grid, THREADS, LP_SMEM_BYTES, st>>>(mB, mBl, mX, mXl, a);
+    else if (a.need_ll) k_hlr_tc<true><<<grid, GTHREADS, SMEM_BYTES, st>>>(mB, mX, a);
+    else k_hlr_tc<false><<<grid, GTHREADS, SMEM_BYTES, st>>>(mB, mX, a);
     prof_end(BK_PROF_GRAD, st);
     BK_LAUNCH_CHECK();
     *part_g = pg; *part_ll = pl; *n_split = ns;

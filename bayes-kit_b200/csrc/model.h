@@ -14,8 +14,9 @@ struct Model {
     __nv_bfloat16* P_lo = nullptr;  // [Dp, Dp] bf16(P - P_hi)
     int64_t Dp = 0;                 // D rounded up to 128
     __nv_bfloat16* Xb = nullptr;    // [Np, 128] bf16(X), zero padded      (fp32 HIER_LOGREG: tcgen05 operands)
-    __nv_bfloat16* XbT = nullptr;   // [128, Np] its transpose
+    __nv_bfloat16* Xlo = nullptr;   // [Np, 128] bf16(X - Xb): split-precision logits
     float* yp = nullptr;            // [Np] responses, zero padded
+    float* yh = nullptr;            // [Np] responses - 1/2 (0 on padded rows)
     bool separable() const {
         return d.kind == BK_MODEL_ISO_GAUSS || d.kind == BK_MODEL_DIAG_GAUSS;
     }
@@ -43,7 +44,8 @@ size_t hlr_tc_model_ws_bytes(const bk_model_desc& d);
 int hlr_tc_prepare(Model& m, void* ws, size_t ws_bytes, cudaStream_t st);
 bool hlr_tc_enabled(const Model& m);
 size_t hlr_tc_eval_ws_bytes(const Model& m, int64_t C);
+enum { HLR_TC_GRAD = 0, HLR_TC_GRAD_LL = 1, HLR_TC_LP = 2 };
 int hlr_tc_partial(const Model& m, const float* theta, int64_t C, void* ws, size_t ws_bytes, float** part_g,
-                   float** part_ll, int* n_split, cudaStream_t st);
+                   float** part_ll, int* n_split, cudaStream_t st, int mode);
 
 }  // namespace bk

@@ -275,7 +275,7 @@ int run_generic(const Model& m, GenArgs<T> p, int algo, int* cache_valid, void* 
     const bool fast = algo == ALGO_HMC && model_has_fast_path(m);
     if (!cache_valid || !*cache_valid) {
         if (fast) {   // same convention as inside the loop: tensor-core gradient, precise density
-            rc = model_eval(m, p.theta, p.C, p.lp, p.grad, ews, ebytes, st, false);
+            rc = model_eval(m, p.theta, p.C, nullptr, p.grad, ews, ebytes, st, false);
             if (rc) return rc;
             rc = model_eval(m, p.theta, p.C, p.lp, nullptr, ews, ebytes, st, true);
         } else {
@@ -295,7 +295,7 @@ int run_generic(const Model& m, GenArgs<T> p, int algo, int* cache_valid, void* 
                 // trajectory starts from).  Only the log density that enters the Hamiltonian
                 // must be precise: at the endpoint it is evaluated separately, density only.
                 if (fast) {
-                    rc = model_eval(m, p.q, p.C, p.lp_q, p.grad_q, ews, ebytes, st, /*precise=*/false);
+                    rc = model_eval(m, p.q, p.C, nullptr, p.grad_q, ews, ebytes, st, /*precise=*/false);
                     if (rc) return rc;
                     if (s + 1 == p.L) rc = model_eval(m, p.q, p.C, p.lp_q, nullptr, ews, ebytes, st, true);
                 } else {

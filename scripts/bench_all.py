@@ -51,7 +51,7 @@ if "c3" in which:
     th0 = np.random.default_rng(1).normal(size=(C, Dx + 2)) * 0.1
     s = bk.HMCDiag(model, 0.01, 10, init=th0, seed=0)
     ms = timed(lambda: s.sample_n(1), reps=3, warm=1)
-    print(json.dumps({"workload": f"c3 HMCDiag hier-logreg N={N} Dx={Dx} C={C}/GPU L=10 eps=0.01 fp32 (tcgen05 interior gradients, fp32 CUDA-core endpoint)",
+    print(json.dumps({"workload": f"c3 HMCDiag hier-logreg N={N} Dx={Dx} C={C}/GPU L=10 eps=0.01 fp32 (tcgen05: bf16 gradients at every step, split-precision density at the endpoint)",
           "ms_per_draw": ms, "chain_steps_per_s": C / (ms * 1e-3), "accept": float(s.last_accept.float().mean()),
           "grad_evals_per_s": 10 * C / (ms * 1e-3), "TFLOPs(4NDx per grad)": 10 * C * 4.0 * N * Dx / (ms * 1e-3) / 1e12}), flush=True)
 if "drghmc" in which:
