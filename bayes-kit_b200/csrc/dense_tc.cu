@@ -425,6 +425,13 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                     }
                     __syncwarp();                     // stage may be refilled by the next issue
                 }
+                if (!d_ok && !no_mem) {   // pad dim (last dim-tile only): keep the next operand's padding zero
+                    for (int j = 0; j < NCH * 32; ++j)
+                        if (cbase + j < a.C) {
+                            hw[(int64_t)j * BK] = __float2bfloat16_rn(0.f);
+                            if (lw) lw[(int64_t)j * BK] = __float2bfloat16_rn(0.f);
+                        }
+                }
                 tc_fence_before();
                 mbar_arrive(tempty(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -465,14 +472,14 @@ __global__ void k_pmu(const float* __restrict__ P, const float* __restrict__ mu,
     if (lane == 0) out[r] = (float)s;
 }
 
-// theta [C,D] fp32 -> bf16 hi (/lo) [C,Dp]; pad columns untouched (zeroed once)
+// theta [C,D] fp32 -> bf16 hi (/lo) [C,Dp]; pad columns written as zeros
 __global__ void k_split_rows(const float* __restrict__ x, int64_t C, int D, int Dp,
                              __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C * D) return;
-    int64_t c = i / D;
-    int d = (int)(i % D);
-    float v = x[i];
+    if (i >= C * Dp) return;
+    int64_t c = i / Dp;
+    int d = (int)(i % Dp);
+    float v = d < D ? x[c * D + d] : 0.f;
     __nv_bfloat16 h = __float2bfloat16_rn(v);
     const int64_t o = box_index(c, d, Dp / BK, BN);
     hi[o] = h;
@@ -569,6 +576,14 @@ __global__ void __launch_bounds__(256) k_hmc_begin_tc(HmcTcArgs p, int64_t t, in
         const int64_t xo = box_index(c, e, p.Dp / BK, BN);   // e % 4 == 0: stays inside one box row
         st4_bf16<true>(p.q_hi + xo, 0, 4, hi);
         if (write_lo) st4_bf16<true>(p.q_lo + xo, 0, 4, lo);
+    }
+    // pad dims [D, Dp) of this chain's MMA operand rows must be zero (they meet P's zero padding)
+    for (int b = (D + 3) / 4 + lane; 4 * b < p.Dp; b += 32) {
+        const __nv_bfloat16 zero4[4] = {__float2bfloat16_rn(0.f), __float2bfloat16_rn(0.f), __float2bfloat16_rn(0.f),
+                                        __float2bfloat16_rn(0.f)};
+        const int64_t xo = box_index(c, 4 * b, p.Dp / BK, BN);
+        st4_bf16<true>(p.q_hi + xo, 0, 4, zero4);
+        if (write_lo) st4_bf16<true>(p.q_lo + xo, 0, 4, zero4);
     }
     kin = warp_sum(kin);
     if (lane == 0) p.h0[c] = p.lp[c] - 0.5f * kin;
@@ -768,9 +783,7 @@ int dense_tc_grad(const Model& m, const float* theta, int64_t C, float* grad, vo
     __nv_bfloat16* lo = ar.take<__nv_bfloat16>(nb);
     if (!ar.ok()) { set_error("dense_tc_grad: workspace too small"); return BK_E_WORKSPACE; }
     const int D = (int)m.d.dims;
-    BK_CUDA(cudaMemsetAsync(hi, 0, nb * 2, st));
-    BK_CUDA(cudaMemsetAsync(lo, 0, nb * 2, st));
-    tc::k_split_rows<<<(unsigned)((C * D + 255) / 256), 256, 0, st>>>(theta, C, D, (int)m.Dp, hi, lo);
+    tc::k_split_rows<<<(unsigned)((C * m.Dp + 255) / 256), 256, 0, st>>>(theta, C, D, (int)m.Dp, hi, lo);
     BK_LAUNCH_CHECK();
     tc::StepArgs a;
     memset(&a, 0, sizeof(a));
@@ -804,12 +817,8 @@ int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* 
         if (rc) return rc;
         if (cache_valid) *cache_valid = 1;
     }
-    // pad dims [D, Dp) and pad chains of the bf16 operands must be zero / finite
-    if (m.Dp != D || (C % tc::BN) != 0) {
-        BK_CUDA(cudaMemsetAsync(qhi[0], 0, nb * 2, st));
-        BK_CUDA(cudaMemsetAsync(qhi[1], 0, nb * 2, st));
-        BK_CUDA(cudaMemsetAsync(qlo, 0, nb * 2, st));
-    }
+    // pad dims [D, Dp) of the bf16 operands are zeroed by the kernels that write them (begin, STEP
+    // epilogue); rows of pad chains only feed output columns nobody reads
     tc::HmcTcArgs h;
     memset(&h, 0, sizeof(h));
     h.theta = theta; h.lp = lp; h.grad = grad; h.gq = gq; h.h0 = h0;

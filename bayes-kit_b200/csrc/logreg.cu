@@ -157,17 +157,29 @@ __global__ void k_hlr_finish(const T* __restrict__ theta, const T* __restrict__ 
         sr += r;
         ss = fma(r, r, ss);
         if (grad) {
-            T g = T(0);
-            for (int s = 0; s < n_split; ++s) g += part_g[((int64_t)s * C + c) * Dx + j];
-            grad[c * D + j] = g - e2 * r;
+            // four interleaved partial sums (independent loads in flight), combined in a fixed order
+            T g0 = T(0), g1 = T(0), g2 = T(0), g3 = T(0);
+            const T* pg = part_g + c * Dx + j;
+            const int64_t step = C * (int64_t)Dx;
+            int s = 0;
+            for (; s + 4 <= n_split; s += 4) {
+                const T a0 = pg[(s + 0) * step], a1 = pg[(s + 1) * step], a2 = pg[(s + 2) * step],
+                        a3 = pg[(s + 3) * step];
+                g0 += a0; g1 += a1; g2 += a2; g3 += a3;
+            }
+            for (; s < n_split; ++s) g0 += pg[s * step];
+            grad[c * D + j] = ((g0 + g1) + (g2 + g3)) - e2 * r;
         }
     }
     sr = warp_sum(sr);
     ss = warp_sum(ss);
+    T ll = T(0);
+    if (lp) {   // slices over lanes, then the (deterministic) butterfly
+        for (int s = lane; s < n_split; s += 32) ll += part_ll[(int64_t)s * C + c];
+        ll = warp_sum(ll);
+    }
     if (lane == 0) {
         if (lp) {
-            T ll = T(0);
-            for (int s = 0; s < n_split; ++s) ll += part_ll[(int64_t)s * C + c];
             lp[c] = ll - T(Dx) * lam - T(0.5) * e2 * ss - T(0.5) * mu * mu - T(0.5) * ep2 + lam;
         }
         if (grad) {
@@ -214,7 +226,7 @@ static int hlr_eval_t(const Model& m, const T* theta, int64_t C, T* lp, T* grad,
             const int mode = precise ? HLR_TC_LP : (no_ll ? HLR_TC_GRAD : HLR_TC_GRAD_LL);
             int rc = hlr_tc_partial(m, theta, C, ws, ws_bytes, &pg, &pl, &ns, st, mode);
             if (rc) return rc;
-            k_hlr_finish<float><<<(unsigned)((C * 32 + 255) / 256), 256, 0, st>>>(theta, pg, pl, C, Dx, D, ns, lp,
+            k_hlr_finish<float><<<(unsigned)((C * 32 + 63) / 64), 64, 0, st>>>(theta, pg, pl, C, Dx, D, ns, lp,
                                                                                  precise ? nullptr : grad);
             BK_LAUNCH_CHECK();
             return BK_OK;
@@ -251,7 +263,7 @@ static int hlr_eval_t(const Model& m, const T* theta, int64_t C, T* lp, T* grad,
         k_hlr_partial<T, false><<<grid, 256, smem, st>>>((const T*)m.d.X, (const T*)m.d.y, theta, C, N, Dx, D, rows, pg, pl);
     prof_end(BK_PROF_GRAD, st);
     BK_LAUNCH_CHECK();
-    k_hlr_finish<T><<<(unsigned)((C * 32 + 255) / 256), 256, 0, st>>>(theta, pg, pl, C, Dx, D, ns, lp, grad);
+    k_hlr_finish<T><<<(unsigned)((C * 32 + 63) / 64), 64, 0, st>>>(theta, pg, pl, C, Dx, D, ns, lp, grad);
     BK_LAUNCH_CHECK();
     return BK_OK;
 }

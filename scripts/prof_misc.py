@@ -1,4 +1,4 @@
-"""Small profiling drivers: python scripts/prof_misc.py {c1|smc|ess|acf}"""
+"""Small profiling drivers: python scripts/prof_misc.py {c1|smc|c3|ess|acf}"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -14,8 +14,14 @@ elif w == "smc":
     smc = bk.TemperedLikelihoodSMC(model, M, T, torch.randn(M, D, device="cuda"), bk.metropolis_kernel(0.2),
                                    resample="systematic", seed=1)
     for n in range(1, 5): smc.transition(n)
+elif w == "c3":
+    from oracle.models import HierLogReg
+    N, Dx, C = 100_000, 100, 1024
+    X, y = HierLogReg.c3_data(N, Dx, seed=0)
+    s = bk.HMCDiag(bk.HierLogReg(X, y), 0.01, 10, init=np.random.default_rng(1).normal(size=(C, Dx + 2)) * 0.1, seed=0)
+    s.sample_n(3)
 elif w in ("ess", "acf"):
-    N, S = 10000, 4096
+    N, S = 10000, 25600 if w == "ess" else 4096
     g = torch.Generator(device="cuda"); g.manual_seed(0)
     phi = torch.rand(S, device="cuda", generator=g) * 0.9
     x = torch.empty(N, S, device="cuda"); cur = torch.randn(S, device="cuda", generator=g)
