@@ -306,7 +306,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_bw, "unit": "GB/s",
                 "frac": (achieved / peak_bw) if achieved else None,
                 # ncu --set full, profiles/: dram read+write per STEP launch (incl. the bf16 operand copy)
-                "traffic": 1.31e9 if C == CHAINS_PER_GPU else None,
+                "traffic": 1.034e9 if C == CHAINS_PER_GPU else None,
                 "kernel": "k_dense_tc STEP mode (tcgen05 gradient GEMM + fused leapfrog epilogue)",
                 "launches_timed": int(sn.value), "avg_launch_ms": s_avg_ms,
                 "share_of_step": sms_.value / ms if ms else None, "peak_source": peak_src,
