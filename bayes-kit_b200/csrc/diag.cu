@@ -23,20 +23,43 @@ constexpr int ACF_TT = 4;    // consecutive draws per thread (register tile)
 constexpr int ACF_PAD = 16;  // zero padding behind the series in shared memory
 
 // ---- moments -------------------------------------------------------------------
-// one-pass shifted sums (shift = first draw) in fp64
-__global__ void k_moments_thread(SeriesView v, double* __restrict__ mean, double* __restrict__ var) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= v.n_series) return;
-    const double sh = v.at(s, 0);
+// one-pass shifted sums (shift = first draw) in fp64.
+// Neighbouring series adjacent in memory (the samplers' [draws, chains, params] layout): a block
+// owns 32 adjacent series; warp w walks draws w, w+8, ... (each load = one 128-byte segment, four
+// in flight per thread) and the 8 slices are combined in shared memory in a fixed order.
+constexpr int MOM_SLICES = 8;
+__global__ void __launch_bounds__(32 * MOM_SLICES) k_moments_thread(SeriesView v, double* __restrict__ mean,
+                                                                     double* __restrict__ var) {
+    __shared__ double p1[MOM_SLICES][32], p2[MOM_SLICES][32];
+    const int sx = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int64_t s = (int64_t)blockIdx.x * 32 + sx;
+    const bool ok = s < v.n_series;
+    const int64_t ss = ok ? s : v.n_series - 1;
+    const double sh = v.at(ss, 0);
     double s1 = 0, s2 = 0;
-    for (int64_t t = 0; t < v.N; ++t) {
-        double d = v.at(s, t) - sh;
+    int64_t t = sl;
+    for (; t + 3 * MOM_SLICES < v.N; t += 4 * MOM_SLICES) {
+        const double d0 = v.at(ss, t) - sh, d1 = v.at(ss, t + MOM_SLICES) - sh,
+                     d2 = v.at(ss, t + 2 * MOM_SLICES) - sh, d3 = v.at(ss, t + 3 * MOM_SLICES) - sh;
+        s1 += (d0 + d1) + (d2 + d3);
+        s2 = fma(d0, d0, s2); s2 = fma(d1, d1, s2); s2 = fma(d2, d2, s2); s2 = fma(d3, d3, s2);
+    }
+    for (; t < v.N; t += MOM_SLICES) {
+        const double d = v.at(ss, t) - sh;
         s1 += d;
         s2 = fma(d, d, s2);
     }
-    const double n = (double)v.N;
-    if (mean) mean[s] = sh + s1 / n;
-    if (var) var[s] = (s2 - s1 * s1 / n) / (n - 1.0);
+    p1[sl][sx] = s1;
+    p2[sl][sx] = s2;
+    __syncthreads();
+    if (sl == 0 && ok) {
+        double a = 0, b = 0;
+#pragma unroll
+        for (int i = 0; i < MOM_SLICES; ++i) { a += p1[i][sx]; b += p2[i][sx]; }
+        const double n = (double)v.N;
+        if (mean) mean[s] = sh + a / n;
+        if (var) var[s] = (b - a * a / n) / (n - 1.0);
+    }
 }
 
 __global__ void k_moments_warp(SeriesView v, double* __restrict__ mean, double* __restrict__ var) {
@@ -235,7 +258,7 @@ int bk_chain_moments(const void* x, int32_t dtype, const bk_series_layout* layou
     // neighbouring series adjacent in memory -> one thread per series is coalesced;
     // otherwise a warp walks one series along the draw axis
     if (layout->n_inner > 1 && layout->inner_stride == 1 && layout->draw_stride != 1)
-        k_moments_thread<<<(unsigned)((n_series + 127) / 128), 128, 0, st>>>(v, mean_out, var_out);
+        k_moments_thread<<<(unsigned)((n_series + 31) / 32), 32 * MOM_SLICES, 0, st>>>(v, mean_out, var_out);
     else
         k_moments_warp<<<(unsigned)((n_series * 32 + 255) / 256), 256, 0, st>>>(v, mean_out, var_out);
     BK_LAUNCH_CHECK();

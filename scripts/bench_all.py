@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bayes_kit_b200 as bk
 HBM = 6548.5  # GB/s measured (MEASURED_PEAKS.json)
-which = sys.argv[1:] or ["c1", "c1mala", "c2mala", "c3", "drghmc", "c4", "c5"]
+which = sys.argv[1:] or ["c1", "c1mala", "c2mala", "c3", "drghmc", "c4", "c5", "acf"]
 
 def timed(fn, reps=5, warm=2):
     for _ in range(warm): fn()
@@ -107,3 +107,18 @@ if "c5" in which:
             ms2 = timed(f_rhat, reps=3, warm=1)
             out.update({"rhat_ms": ms2, "rhat_GBps": Cn * P * N * 4 / 1e9 / (ms2 * 1e-3)})
         print(json.dumps(out), flush=True)
+
+if "acf" in which:
+    N, S_ = 10000, 8192
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    phi = torch.rand(S_, device="cuda", generator=g) * 0.9
+    x = torch.empty(N, S_, device="cuda"); cur = torch.randn(S_, device="cuda", generator=g)
+    for t in range(N):
+        cur = phi * cur + torch.randn(S_, device="cuda", generator=g); x[t] = cur
+    xs = x.t().contiguous()                      # [series, draws]
+    ms = timed(lambda: bk.autocorr(xs), reps=3, warm=1)
+    a = bk.autocorr(xs[:64])
+    ref = torch.stack([phi[:64] ** k for k in range(4)], 1)      # AR(1): rho_k = phi^k
+    print(json.dumps({"workload": f"c5 autocorr (all {N} lags, FFT length 32768) series={S_} fp32 in / fp64", "ms": ms,
+          "series_per_s": S_ / (ms * 1e-3), "GBps_algorithmic(N*(4+8)B)": S_ * N * 12 / 1e9 / (ms * 1e-3),
+          "max_abs_err_first_lags_vs_AR1": float((a[:, :4] - ref.double()).abs().max())}), flush=True)
