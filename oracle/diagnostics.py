@@ -110,6 +110,36 @@ def split_rhat(chains):
     return rhat(split_chains(chains))
 
 
+def rank_chains(chains):
+    """rhat.py:27-59: ascending ranks from 1 over the concatenation of all chains
+    (``argsort().argsort() + 1``), handed back chain by chain.  Ties: the
+    reference's default (unstable) sort leaves their order implementation
+    defined; a STABLE sort is used here (ties ranked in flattened order) -- the
+    rule the device sort follows too.  No reference test exercises ties."""
+    if len(chains) == 0:
+        return chains
+    flat = np.concatenate([np.asarray(c, dtype=np.float64) for c in chains])
+    ranks = (flat.argsort(kind="stable").argsort(kind="stable") + 1).astype(np.float64)
+    out, i = [], 0
+    for c in chains:
+        out.append(ranks[i:i + len(c)])
+        i += len(c)
+    return out
+
+
+def rank_normalize_chains(chains):
+    """rhat.py:62-108: ``norm.ppf((rank - 0.325) / (S - 0.25))`` with S the total
+    number of draws (the code's constants; its docstring says 3/8)."""
+    from scipy.special import ndtri   # == scipy.stats.norm.ppf for loc 0, scale 1
+    S = sum(len(c) for c in chains)
+    return [ndtri((r - 0.325) / (S - 0.25)) for r in rank_chains(chains)]
+
+
+def rank_normalized_rhat(chains):
+    """rhat.py:205-236."""
+    return split_rhat(rank_normalize_chains(chains))
+
+
 # ---- batch helpers ---------------------------------------------------------
 def autocorr_batch(x):
     """x [S, N] -> [S, N]."""

@@ -221,6 +221,22 @@ def gen_diagnostics(bk):
     _check("rhat", od.rhat_batch(ch), rh, 1e-13)
     _check("split_rhat", [od.split_rhat(list(ch[:, :, p])) for p in range(3)], srh, 1e-13)
     out.update(rhat_chains=ch, rhat=rh, split_rhat=srh)
+    # rank-normalised family (rhat.py:27-108, 205-236): continuous draws -> no ties
+    from bayes_kit.rhat import (rank_chains as r_rank, rank_normalize_chains as r_rn,
+                                rank_normalized_rhat as r_rnr)
+    rk = np.stack([np.stack(r_rank(list(ch[:, :, p]))) for p in range(3)], -1)          # [8, 500, 3]
+    rn = np.stack([np.array(r_rn(list(ch[:, :, p]))) for p in range(3)], -1)
+    rnr = np.array([r_rnr(list(ch[:, :, p])) for p in range(3)])
+    _check("rank_chains", np.stack([np.stack(od.rank_chains(list(ch[:, :, p]))) for p in range(3)], -1), rk, 0)
+    _check("rank_normalize", np.stack([np.stack(od.rank_normalize_chains(list(ch[:, :, p]))) for p in range(3)], -1),
+           rn, 1e-14)
+    _check("rank_normalized_rhat", [od.rank_normalized_rhat(list(ch[:, :, p])) for p in range(3)], rnr, 1e-13)
+    heavy = rng.standard_cauchy(size=(4, 101))            # odd length, heavy tails (the use case, rhat.py:211-214)
+    heavy[2] += 3.0
+    out.update(ranks=rk, rank_normalized=rn, rank_normalized_rhat=rnr, cauchy_chains=heavy,
+               cauchy_split_rhat=r_split_rhat(list(heavy)), cauchy_rank_normalized_rhat=r_rnr(list(heavy)),
+               cauchy_rank_normalized=np.array(r_rn(list(heavy))))
+    _check("cauchy rank_normalized_rhat", od.rank_normalized_rhat(list(heavy)), r_rnr(list(heavy)), 1e-13)
     np.savez_compressed(os.path.join(OUT, "diagnostics.npz"), **out)
 
 

@@ -87,3 +87,18 @@ def test_rhat():
     _close(od.rhat_batch(z["rhat_chains"]), z["rhat"])
     ch = z["rhat_chains"]
     _close([od.split_rhat(list(ch[:, :, p])) for p in range(3)], z["split_rhat"])
+
+
+def test_rank_normalized_rhat_golden():
+    """Oracle restatement vs the live reference's recorded outputs (rhat.py:27-108, 205-236)."""
+    z = golden("diagnostics")
+    ch = z["rhat_chains"]
+    for p in range(3):
+        chains = list(ch[:, :, p])
+        assert np.array_equal(np.stack(od.rank_chains(chains)), z["ranks"][:, :, p])
+        _close(np.stack(od.rank_normalize_chains(chains)), z["rank_normalized"][:, :, p])
+        _close(od.rank_normalized_rhat(chains), z["rank_normalized_rhat"][p])
+    heavy = list(z["cauchy_chains"])
+    _close(od.split_rhat(heavy), z["cauchy_split_rhat"])
+    _close(np.stack(od.rank_normalize_chains(heavy)), z["cauchy_rank_normalized"])
+    _close(od.rank_normalized_rhat(heavy), z["cauchy_rank_normalized_rhat"])

@@ -98,3 +98,47 @@ def test_accept_rule():  # test_metropolis.py:32-52 (uniform draw 0.5)
     # log(0) = -inf always accepts (metropolis.py:36-38)
     _, _, a = osm.metropolis_rw(model, np.array([0.1]), np.array([[5.0]]), np.array([0.0]), 1.0)
     assert a[0]
+
+
+# ---- rank-normalised R-hat family -------------------------------------
+def _rank_norm(r, S):  # test_rhat.py:133-134
+    from scipy.stats import norm
+    return norm.ppf((r - 0.325) / (S - 0.25))
+
+
+def test_split_chains():  # test_rhat.py:71-79
+    eq = lambda want, got: [np.testing.assert_array_equal(w, g) for w, g in zip(want, got)] and None
+    assert od.split_chains([]) == []
+    eq([[1], []], od.split_chains([[1]]))
+    eq([[1], [2]], od.split_chains([[1, 2]]))
+    eq([[1, 2], [3]], od.split_chains([[1, 2, 3]]))
+    eq([[1, 2], [3], [4, 5], [6, 7]], od.split_chains([[1, 2, 3], [4, 5, 6, 7]]))
+
+
+def test_split_rhat():  # test_rhat.py:82-110
+    np.testing.assert_allclose(od.rhat([[1, 2], [3, 4]]), od.split_rhat([[1, 2, 3, 4]]))
+    np.testing.assert_allclose(od.rhat([[1, -2, 3], [4, 5, 6], [7, 8], [9, 12]]),
+                               od.split_rhat([[1, -2, 3, 4, 5, 6], [7, 8, 9, 12]]))
+    for bad in ([], [[1, 2, 3]], [[1, 2, 3, 4], [1, 2, 3]]):
+        with pytest.raises(ValueError):
+            od.split_rhat(bad)
+
+
+def test_rank_chains():  # test_rhat.py:113-126
+    assert od.rank_chains([]) == []
+    for want, chains in [([[1]], [[2.3]]), ([[2, 3, 1]], [[3.9, 5.2, 2.1]]), ([[2], [1]], [[4.2], [1.9]]),
+                         ([[2, 3], [5, 4], [1, 6]], [[4.2, 5.7], [7.2, 6.1], [-12.9, 107]])]:
+        for w, g in zip(want, od.rank_chains(chains)):
+            np.testing.assert_array_equal(w, g)
+
+
+def test_rank_normalize_and_rhat():  # test_rhat.py:137-196
+    np.testing.assert_array_equal([[_rank_norm(1, 1)]], od.rank_normalize_chains([[32.7]]))
+    got = od.rank_normalize_chains([[3.9, 3.1], [2.2, 5.9]])
+    np.testing.assert_array_equal([[_rank_norm(3, 4), _rank_norm(2, 4)], [_rank_norm(1, 4), _rank_norm(4, 4)]], got)
+    rn = [_rank_norm(i, 8) for i in range(1, 9)]
+    np.testing.assert_allclose(od.split_rhat([[rn[1], rn[2], rn[6], rn[7]], [rn[0], rn[3], rn[5], rn[4]]]),
+                               od.rank_normalized_rhat([[2, 3, 7, 8], [1, 4, 6, 5]]))
+    for bad in ([], [[1.01, 1.2, 1.3]], [[1, 2, 3], [4]]):
+        with pytest.raises(ValueError):
+            od.rank_normalized_rhat(bad)
