@@ -18,7 +18,8 @@ from .mala import MALA
 from .metropolis import (GaussianRW, Metropolis, MetropolisHastings, metropolis_accept_test,
                          metropolis_hastings_accept_test)
 from .models import DensePrecGauss, DiagGauss, GaussPriorLik, HierLogReg, IsoGauss, StdNormal
-from .rhat import chain_moments, rhat
+from .rhat import (chain_moments, rank_chains, rank_normalize_chains, rank_normalized_rhat, rhat,
+                   split_chains, split_rhat)
 from .smc import TemperedLikelihoodSMC, metropolis_kernel
 
 __all__ = [
@@ -27,4 +28,6 @@ __all__ = [
     # device-side additions
     "GaussianRW", "metropolis_kernel", "models", "dist", "IsoGauss", "StdNormal", "DiagGauss",
     "DensePrecGauss", "GaussPriorLik", "HierLogReg", "chain_moments",
+    # rhat.py's split / rank-normalised family (not re-exported by the reference's __init__)
+    "split_chains", "split_rhat", "rank_chains", "rank_normalize_chains", "rank_normalized_rhat",
 ]

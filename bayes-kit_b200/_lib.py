@@ -81,6 +81,8 @@ _SIGNATURES = {
     "bk_smc_resample_indices_dev": (C.c_int, [vp, i64, i32, i32, vp, vp, C.POINTER(Rng), i64, i64, vp, vp,
                                               vp, sz, vp]),
     "bk_gather_rows": (C.c_int, [vp, vp, i64, i64, i32, vp, vp]),
+    "bk_rank_normalize_workspace_bytes": (sz, [i64, i32]),
+    "bk_rank_normalize": (C.c_int, [vp, i32, C.POINTER(SeriesLayout), vp, vp, vp, sz, vp]),
     "bk_autocorr_workspace_bytes": (sz, [i64, i64]),
     "bk_autocorr": (C.c_int, [vp, i32, C.POINTER(SeriesLayout), vp, vp, sz, vp]),
     "bk_iat_ess": (C.c_int, [vp, i32, C.POINTER(SeriesLayout), i32, vp, vp, vp, sz, vp]),

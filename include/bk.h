@@ -232,6 +232,18 @@ typedef struct bk_series_layout {
     int64_t n_series, n_draws, n_inner, outer_stride, inner_stride, draw_stride;
 } bk_series_layout;
 
+/* Rank normalisation of ONE parameter (rhat.py:27-108): the layout's series are
+ * that parameter's chains (n_series chains x n_draws draws each); ranks are taken
+ * over the concatenation of the chains in series order (np.concatenate,
+ * rhat.py:51), ascending from 1, ties in flattened order (stable; the reference's
+ * tie order is implementation defined).  ranks_out / z_out [n_series * n_draws]
+ * f64 in that same flattened order (either may be NULL):
+ *   z = Phi^-1((rank - 0.325) / (S - 0.25)),  S = n_series * n_draws   (rhat.py:106)
+ * Hand-written stable LSD radix sort + normcdfinv; S < 2^32. */
+BK_API size_t bk_rank_normalize_workspace_bytes(int64_t n_total, int32_t dtype);
+BK_API int bk_rank_normalize(const void* x, int32_t dtype, const bk_series_layout* layout,
+                      double* ranks_out, double* z_out, void* ws, size_t ws_bytes, void* stream);
+
 BK_API size_t bk_autocorr_workspace_bytes(int64_t n_series, int64_t N);
 /* autocorr.py:6-33 -- all N lags of the biased estimator, fp64 accumulate;
  * out [n_series, N] f64 */

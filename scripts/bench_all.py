@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bayes_kit_b200 as bk
 HBM = 6548.5  # GB/s measured (MEASURED_PEAKS.json)
-which = sys.argv[1:] or ["c1", "c1mala", "c2mala", "c3", "drghmc", "c4", "c5", "acf"]
+which = sys.argv[1:] or ["c1", "c1mala", "c2mala", "c3", "drghmc", "c4", "c5", "acf", "rnrhat"]
 
 def timed(fn, reps=5, warm=2):
     for _ in range(warm): fn()
@@ -122,3 +122,15 @@ if "acf" in which:
     print(json.dumps({"workload": f"c5 autocorr (all {N} lags, FFT length 32768) series={S_} fp32 in / fp64", "ms": ms,
           "series_per_s": S_ / (ms * 1e-3), "GBps_algorithmic(N*(4+8)B)": S_ * N * 12 / 1e9 / (ms * 1e-3),
           "max_abs_err_first_lags_vs_AR1": float((a[:, :4] - ref.double()).abs().max())}), flush=True)
+
+if "rnrhat" in which:
+    N, Cn, P = 10000, 4096, 2
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    x = torch.randn(N, Cn, P, device="cuda", generator=g)          # [draws, chains, params], the samplers' layout
+    ms = timed(lambda: bk.rank_normalized_rhat(x, draws_first=True), reps=3, warm=1)
+    ms_s = timed(lambda: bk.split_rhat(x, draws_first=True), reps=3, warm=1)
+    r = bk.rank_normalized_rhat(x, draws_first=True)
+    n = N * Cn * P
+    print(json.dumps({"workload": f"rank_normalized_rhat {Cn} chains x {N} draws x {P} params fp32 (radix sort of {N*Cn/1e6:.0f} M keys per parameter)",
+          "ms": ms, "M_draws_per_s": n / (ms * 1e-3) / 1e6, "GBps_sort_traffic(80B/key)": n * 80 / 1e9 / (ms * 1e-3),
+          "split_rhat_ms": ms_s, "split_rhat_GBps": n * 4 / 1e9 / (ms_s * 1e-3), "value": [float(v) for v in r]}), flush=True)

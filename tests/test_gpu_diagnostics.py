@@ -13,6 +13,15 @@ pytestmark = pytest.mark.gpu
 TOL = dict(rtol=1e-9, atol=1e-10)
 
 
+def oracle_rhat(chains):
+    return od.rhat([np.asarray(c, dtype=np.float64) for c in chains])
+
+
+def od_rank(x):
+    """[chains, draws] -> ranks in the same shape (oracle, stable ties)."""
+    return np.stack(od.rank_chains(list(x)))
+
+
 @pytest.mark.parametrize("tag", ["n37", "n1000", "n10000"])
 def test_golden(bk, tag):
     z = golden("diagnostics")
@@ -115,3 +124,69 @@ def test_autocorr_both_paths(bk, mode, monkeypatch):
         np.testing.assert_allclose(np_(bk.autocorr(x)), od.autocorr_batch(x), **TOL)
     x32 = torch.as_tensor(od.sample_ar1(0.5, 5000, rng), dtype=torch.float32, device="cuda")
     np.testing.assert_allclose(np_(bk.autocorr(x32)), od.autocorr(np_(x32).astype(np.float64)), **TOL)
+
+
+# ---- split / rank-normalised R-hat (reference rhat.py:9-108, 174-236) --------------
+def test_split_and_rank_normalized_rhat_golden(bk):
+    z = golden("diagnostics")
+    ch = z["rhat_chains"]                                    # [8, 500, 3]
+    for dt, tol in ((torch.float64, 1e-9), ):
+        x = torch.as_tensor(ch, dtype=dt, device="cuda")
+        np.testing.assert_allclose(np_(bk.split_rhat(x)), z["split_rhat"], rtol=tol)
+        rk = np_(bk.rank_chains(x))
+        assert np.array_equal(rk, z["ranks"])                # bit-exact integer work
+        rn = np_(bk.rank_normalize_chains(x))
+        np.testing.assert_allclose(rn, z["rank_normalized"], rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(np_(bk.rank_normalized_rhat(x)), z["rank_normalized_rhat"], rtol=tol)
+        # the samplers' [draws, chains, params] layout, consumed in place
+        xd = x.permute(1, 0, 2).contiguous()
+        np.testing.assert_allclose(np_(bk.split_rhat(xd, draws_first=True)), z["split_rhat"], rtol=tol)
+        assert np.array_equal(np_(bk.rank_chains(xd, draws_first=True)), z["ranks"])
+        np.testing.assert_allclose(np_(bk.rank_normalized_rhat(xd, draws_first=True)), z["rank_normalized_rhat"],
+                                   rtol=tol)
+    heavy = z["cauchy_chains"]                               # [4, 101]: odd length, heavy tails
+    assert abs(bk.split_rhat(list(heavy)) - float(z["cauchy_split_rhat"])) <= 1e-9 * float(z["cauchy_split_rhat"])
+    np.testing.assert_allclose(np.stack(bk.rank_normalize_chains(list(heavy))), z["cauchy_rank_normalized"],
+                               rtol=1e-12, atol=1e-13)
+    got = bk.rank_normalized_rhat(list(heavy))
+    assert abs(got - float(z["cauchy_rank_normalized_rhat"])) <= 1e-9
+
+
+def test_rank_family_reference_known_answers(bk):
+    """test_rhat.py:71-196 through the device path."""
+    from scipy.stats import norm
+    rn = lambda r, S: norm.ppf((r - 0.325) / (S - 0.25))
+    assert bk.rank_chains([]) == [] and bk.rank_normalize_chains([]) == []
+    for want, chains in [([[1]], [[2.3]]), ([[2, 3, 1]], [[3.9, 5.2, 2.1]]), ([[2], [1]], [[4.2], [1.9]]),
+                         ([[2, 3], [5, 4], [1, 6]], [[4.2, 5.7], [7.2, 6.1], [-12.9, 107]]),
+                         ([[2, 3, 6], [5, 4], [1]], [[4.2, 5.7, 108.0], [7.2, 6.1], [-12.9]])]:   # ragged
+        for w, g in zip(want, bk.rank_chains(chains)):
+            np.testing.assert_array_equal(w, g)
+    np.testing.assert_allclose(bk.rank_normalize_chains([[32.7]])[0], [rn(1, 1)], rtol=1e-13)
+    got = bk.rank_normalize_chains([[3.9, 3.1], [2.2, 5.9]])
+    np.testing.assert_allclose(np.stack(got), [[rn(3, 4), rn(2, 4)], [rn(1, 4), rn(4, 4)]], rtol=1e-13)
+    np.testing.assert_allclose(oracle_rhat([[1, 2], [3, 4]]), bk.split_rhat([[1, 2, 3, 4]]), rtol=1e-12)
+    np.testing.assert_allclose(oracle_rhat([[1, -2, 3], [4, 5, 6], [7, 8], [9, 12]]),
+                               bk.split_rhat([[1, -2, 3, 4, 5, 6], [7, 8, 9, 12]]), rtol=1e-12)
+    r8 = [rn(i, 8) for i in range(1, 9)]
+    np.testing.assert_allclose(bk.split_rhat([[r8[1], r8[2], r8[6], r8[7]], [r8[0], r8[3], r8[5], r8[4]]]),
+                               bk.rank_normalized_rhat([[2, 3, 7, 8], [1, 4, 6, 5]]), rtol=1e-12)
+    for fn, bad in [(bk.split_rhat, []), (bk.split_rhat, [[1, 2, 3]]), (bk.split_rhat, [[1, 2, 3, 4], [1, 2, 3]]),
+                    (bk.rank_normalized_rhat, []), (bk.rank_normalized_rhat, [[1.01, 1.2, 1.3]]),
+                    (bk.rank_normalized_rhat, [[1, 2, 3], [4]])]:
+        with pytest.raises(ValueError):
+            fn(bad)
+
+
+def test_rank_sort_large_and_ties(bk):
+    """Radix sort at a size that spans many tiles (fp32 and fp64 keys), negative values, and
+    exact ties (rejected MCMC proposals repeat a draw): ties rank in flattened order."""
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((7, 9001)) * np.array([1e-3, 1, 1e3, 1, 1, 1e-20, 1])[:, None]
+    x[3, 100:140] = x[3, 99]                                  # a run of rejections
+    x[5, :10] = 0.0
+    x[5, 3] = -0.0
+    for dt in (torch.float64, torch.float32):
+        xt = torch.as_tensor(x, dtype=dt, device="cuda")
+        want = od_rank(np_(xt).astype(np.float64))
+        assert np.array_equal(np_(bk.rank_chains(xt)), want)
