@@ -139,14 +139,17 @@ __host__ __device__ __forceinline__ double u01d(uint32_t hi, uint32_t lo) {
 }
 
 // 4 standard normals for element block `block` of (chain, draw)
+// (raw2, when given, receives the first two counter-mode words of the block: a caller whose block
+// holds no valid element may spend them on something else, e.g. an accept uniform)
 template <typename T>
 __device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t block, uint32_t chain,
-                                               uint32_t draw, T (&z)[4]);
+                                               uint32_t draw, T (&z)[4], uint32_t* raw2 = nullptr);
 template <>
 __device__ __forceinline__ void philox_normal4<float>(uint64_t seed, uint32_t block, uint32_t chain,
-                                                      uint32_t draw, float (&z)[4]) {
+                                                      uint32_t draw, float (&z)[4], uint32_t* raw2) {
     uint32_t r[4];
     Philox::gen(seed, block, TAG_NORMAL, chain, draw, r);
+    if (raw2) { raw2[0] = r[0]; raw2[1] = r[1]; }
     // Box-Muller on the SFU: __logf / __sincosf have ~2^-21 absolute error on these
     // ranges (angle folded into [-pi, pi)) -- far below the fp32 sampling noise.
     float r0 = sqrtf(-2.0f * __logf(u01(r[0]))), r1 = sqrtf(-2.0f * __logf(u01(r[2])));
@@ -157,9 +160,10 @@ __device__ __forceinline__ void philox_normal4<float>(uint64_t seed, uint32_t bl
 }
 template <>
 __device__ __forceinline__ void philox_normal4<double>(uint64_t seed, uint32_t block, uint32_t chain,
-                                                       uint32_t draw, double (&z)[4]) {
+                                                       uint32_t draw, double (&z)[4], uint32_t* raw2) {
     uint32_t a[4], b[4];
     Philox::gen(seed, block, TAG_NORMAL, chain, draw, a);
+    if (raw2) { raw2[0] = a[0]; raw2[1] = a[1]; }
     Philox::gen(seed, block, TAG_NORMAL_HI, chain, draw, b);
     double r0 = sqrt(-2.0 * log(u01d(a[0], a[1]))), r1 = sqrt(-2.0 * log(u01d(b[0], b[1])));
     double s0, c0, s1, c1;

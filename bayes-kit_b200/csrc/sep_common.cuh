@@ -68,8 +68,9 @@ struct Lanes {
         }
     }
     // standard normals for (chain, draw); invalid slots are 0
+    // raw2 (optional): the first two Philox words of this lane's LAST block (j = J - 1)
     __device__ __forceinline__ void normals(const bk_rng& rng, int64_t C, int64_t chain, int64_t t,
-                                            T (&z)[NE]) const {
+                                            T (&z)[NE], uint32_t* raw2 = nullptr) const {
         if (rng.mode == BK_RNG_INJECTED) {
             load(reinterpret_cast<const T*>(rng.normals) + (t * C + chain) * (int64_t)D, z, T(0));
         } else {
@@ -79,7 +80,7 @@ struct Lanes {
             for (int j = 0; j < J; ++j) {
                 int blk = lane + G * j;
                 T q[4];
-                philox_normal4<T>(rng.seed, (uint32_t)blk, gc, gd, q);
+                philox_normal4<T>(rng.seed, (uint32_t)blk, gc, gd, q, j == J - 1 ? raw2 : nullptr);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) z[4 * j + i] = (4 * blk + i < D) ? q[i] : T(0);
             }

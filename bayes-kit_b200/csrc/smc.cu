@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(128) k_smc_move_weight(SmcArgs<T> a) {
     ln.load(a.pl, pl, T(0));
     ln.load(a.m0, m0, T(0));
     ln.load(a.p0, p0, T(0));
+    const bool spare_block = a.rng.mode == BK_RNG_PHILOX && 4 * (G * J - 1) >= a.D;
     auto particle = [&](int64_t it) { const int64_t r = g0 + it * n_groups; return r < a.M ? r : a.M - 1; };
     auto row_of = [&](int64_t m) { return a.src_idx ? a.src_idx[m] : m; };
     T nx[NE];                                  // particle of the next visit
@@ -76,16 +77,28 @@ __global__ void __launch_bounds__(128) k_smc_move_weight(SmcArgs<T> a) {
         // thetas[idxs] of the previous importance_resample (smc.py:75) is folded into this read
         if (it + 1 < n_it) ln.load(a.src + row_nn * (int64_t)a.D, nx, T(0));
         if (it + 2 < n_it) row_nn = row_of(particle(it + 2));
-        ln.normals(a.rng, a.M, m, 0, z);
+        uint32_t raw2[2] = {0u, 0u};
+        ln.normals(a.rng, a.M, m, 0, z, raw2);
 #pragma unroll
         for (int k = 0; k < NE; ++k) st[k] = A::add(th[k], A::mul(a.scale, z[k]));  // smc.py:81
         T ll_c, pr_c, ll_s, pr_s;
         gpl_terms<T, G, J>(th, mu, pl, m0, p0, ll_c, pr_c);
         gpl_terms<T, G, J>(st, mu, pl, m0, p0, ll_s, pr_s);
         const T lp_c = A::add(A::mul(ll_c, a.t0), pr_c), lp_s = A::add(A::mul(ll_s, a.t0), pr_s);
+        // accept uniform: when the group's last element block is pure padding (4 (G J - 1) >= D), its
+        // Philox words are unused by the proposal and serve as the uniform -- one counter-mode call per
+        // lane and particle instead of two.  Otherwise (and for injected streams) the dedicated stream.
         T lu = T(0);
-        if (ln.lane == 0) lu = log_u(ln.uniform(a.rng, a.M, m, 0, 0));
-        lu = __shfl_sync(0xffffffffu, lu, 0, G);
+        if (spare_block) {
+            if (ln.lane == G - 1) {
+                if constexpr (sizeof(T) == 4) lu = log_u(u01(raw2[0]));
+                else lu = log_u(u01d(raw2[0], raw2[1]));
+            }
+            lu = __shfl_sync(0xffffffffu, lu, G - 1, G);
+        } else {
+            if (ln.lane == 0) lu = log_u(ln.uniform(a.rng, a.M, m, 0, 0));
+            lu = __shfl_sync(0xffffffffu, lu, 0, G);
+        }
         const bool acc = lu < A::sub(lp_s, lp_c);  // smc.py:85
         if (acc) {
 #pragma unroll

@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="chains per sample_host chunk (0: library default)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -254,7 +255,8 @@ def main():
     def e2e_step(k):
         # public API: chain state in from host buffer k&1, draw + log density out to the other;
         # H2D, kernels and D2H of successive chain chunks overlap on three streams
-        sampler.sample_host(host_buf[k & 1], out=(host_buf[(k + 1) & 1], host_lp))
+        sampler.sample_host(host_buf[k & 1], out=(host_buf[(k + 1) & 1], host_lp),
+                            chunk_chains=args.e2e_chunk or None)
 
     for k in range(2):
         e2e_step(k)
