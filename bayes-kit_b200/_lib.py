@@ -87,6 +87,7 @@ _SIGNATURES = {
     "bk_autocorr": (C.c_int, [vp, i32, C.POINTER(SeriesLayout), vp, vp, sz, vp]),
     "bk_iat_ess": (C.c_int, [vp, i32, C.POINTER(SeriesLayout), i32, vp, vp, vp, sz, vp]),
     "bk_chain_moments": (C.c_int, [vp, i32, C.POINTER(SeriesLayout), vp, vp, vp]),
+    "bk_moments_accumulate": (C.c_int, [vp, i32, i64, i64, i64, vp, vp, vp]),
     "bk_rhat_from_moments": (C.c_int, [vp, vp, vp, i64, i64, i64, vp, vp]),
 }
 

@@ -6,7 +6,7 @@ from typing import Iterator, Optional, Tuple
 import torch
 
 from . import _lib as L
-from ._util import Workspace, make_rng, ptr, resolve_seed, to_dev
+from ._util import Workspace, make_rng, ptr, resolve_seed, stream_ptr, to_dev
 from .models import require_plugin
 
 DrawAndLogP = Tuple[torch.Tensor, torch.Tensor]
@@ -82,13 +82,21 @@ class ChainSampler:
     def theta(self) -> torch.Tensor:
         return self._theta[0] if self._single else self._theta
 
-    def sample_n(self, n: int, normals=None, uniforms=None, keep_draws: bool = True):
+    def sample_n(self, n: int, normals=None, uniforms=None, keep_draws: bool = True, moments: bool = False):
         """Advance every chain n draws in one call.  Returns (draws [n, C, D],
         logp [n, C]) ([n, D], [n] for a single chain); with keep_draws=False only
-        the final state is kept (warm-up) and draws is None."""
+        the final state is kept (warm-up) and draws is None.  ``moments=True``
+        folds the batch into running per-chain, per-dimension mean / variance
+        (``running_moments()``, ``running_rhat()``) -- convergence monitoring
+        without storing or re-reading the chains."""
         n = int(n)
         C_, D = self._C, self._dim
-        draws = torch.empty(n, C_, D, dtype=self.dtype, device=self.device) if keep_draws else None
+        if moments and not keep_draws and n > 16:      # bound the transient draw buffer
+            out_l = []
+            for k in range(0, n, 16):
+                out_l.append(self.sample_n(min(16, n - k), keep_draws=False, moments=True)[1])
+            return None, torch.cat(out_l)
+        draws = torch.empty(n, C_, D, dtype=self.dtype, device=self.device) if (keep_draws or moments) else None
         logp = torch.empty(n, C_, dtype=self.dtype, device=self.device)
         acc = torch.empty(n, C_, dtype=torch.int32, device=self.device)
         if normals is not None:
@@ -100,9 +108,37 @@ class ChainSampler:
             self._launch(n, rng, out)
         self._t += n
         self.last_accept = acc[:, 0] if self._single else acc
+        if moments and n > 0:
+            if getattr(self, "_mom", None) is None:
+                self._mom = [torch.empty(C_, D, dtype=torch.float64, device=self.device),
+                             torch.empty(C_, D, dtype=torch.float64, device=self.device), 0]
+            with torch.cuda.device(self.device):
+                L.check(L.lib().bk_moments_accumulate(
+                    draws.data_ptr(), L.BK_F32 if self.dtype == torch.float32 else L.BK_F64, n, C_ * D,
+                    self._mom[2], self._mom[0].data_ptr(), self._mom[1].data_ptr(), stream_ptr(self.device)))
+            self._mom[2] += n
+            if not keep_draws:
+                draws = None
         if self._single:
-            return (draws[:, 0] if keep_draws else None), logp[:, 0]
+            return (draws[:, 0] if draws is not None else None), logp[:, 0]
         return draws, logp
+
+    def running_moments(self):
+        """(mean [C, D], var [C, D] with ddof=1, n) over every draw taken with
+        ``moments=True`` so far (fp64)."""
+        if getattr(self, "_mom", None) is None or self._mom[2] < 2:
+            raise ValueError("running moments need at least 2 draws taken with moments=True")
+        return self._mom[0], self._mom[1] / (self._mom[2] - 1), self._mom[2]
+
+    def running_rhat(self) -> torch.Tensor:
+        """R-hat per dimension (rhat.py:111-171) from the running moments of this
+        sampler's chains: no pass over stored draws."""
+        from .rhat import _rhat_from
+        mean, var, n = self.running_moments()
+        return _rhat_from(mean, var, None, n)
+
+    def reset_moments(self) -> None:
+        self._mom = None
 
     def sample_host(self, theta_host=None, out=None, chunk_chains: Optional[int] = None):
         """One draw of every chain with HOST buffers, pipelined over chain chunks.

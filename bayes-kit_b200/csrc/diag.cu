@@ -82,6 +82,33 @@ __global__ void k_moments_warp(SeriesView v, double* __restrict__ mean, double* 
     }
 }
 
+// Streaming moments: fold a batch of n draws [n, E] (E = chains x dims, the samplers'
+// output) into running per-element (mean, M2) over n0 earlier draws -- Chan et al.'s pairwise merge,
+// fp64.  One thread per element, coalesced across elements; the accumulators are touched once per
+// BATCH (32 B per element), the draws once (s bytes per element-draw).
+template <typename T>
+__global__ void k_moments_accumulate(const T* __restrict__ draws, int64_t n, int64_t E, int64_t n0,
+                                     double* __restrict__ mean, double* __restrict__ m2) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const double sh = (double)draws[e];            // shift by the batch's first draw
+    double s1 = 0, s2 = 0;
+    for (int64_t t = 0; t < n; ++t) {
+        const double d = (double)draws[t * E + e] - sh;
+        s1 += d;
+        s2 = fma(d, d, s2);
+    }
+    const double nb = (double)n, mb = sh + s1 / nb, m2b = s2 - s1 * s1 / nb;
+    if (n0 == 0) {
+        mean[e] = mb;
+        m2[e] = m2b;
+    } else {
+        const double na = (double)n0, nt = na + nb, delta = mb - mean[e];
+        mean[e] += delta * (nb / nt);
+        m2[e] += m2b + delta * delta * (na * nb / nt);
+    }
+}
+
 // one warp per parameter; moments laid out [n_chains, n_params]
 __global__ void k_rhat(const double* __restrict__ mean, const double* __restrict__ var,
                        const int64_t* __restrict__ lengths, int64_t N, int64_t n_chains,
@@ -261,6 +288,23 @@ int bk_chain_moments(const void* x, int32_t dtype, const bk_series_layout* layou
         k_moments_thread<<<(unsigned)((n_series + 31) / 32), 32 * MOM_SLICES, 0, st>>>(v, mean_out, var_out);
     else
         k_moments_warp<<<(unsigned)((n_series * 32 + 255) / 256), 256, 0, st>>>(v, mean_out, var_out);
+    BK_LAUNCH_CHECK();
+    return BK_OK;
+}
+
+int bk_moments_accumulate(const void* draws, int32_t dtype, int64_t n_draws, int64_t n_elems, int64_t n0,
+                          double* mean_inout, double* m2_inout, void* stream) {
+    BK_CHECK_ARG(draws && mean_inout && m2_inout, "bk_moments_accumulate: null argument");
+    BK_CHECK_ARG(dtype == BK_F32 || dtype == BK_F64, "bk_moments_accumulate: bad dtype %d", dtype);
+    BK_CHECK_ARG(n_draws >= 0 && n_elems >= 0 && n0 >= 0, "bk_moments_accumulate: negative size");
+    if (n_draws == 0 || n_elems == 0) return BK_OK;
+    const unsigned blocks = (unsigned)((n_elems + 255) / 256);
+    if (dtype == BK_F64)
+        k_moments_accumulate<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((const double*)draws, n_draws, n_elems,
+                                                                             n0, mean_inout, m2_inout);
+    else
+        k_moments_accumulate<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)draws, n_draws, n_elems,
+                                                                            n0, mean_inout, m2_inout);
     BK_LAUNCH_CHECK();
     return BK_OK;
 }

@@ -255,6 +255,13 @@ BK_API int bk_iat_ess(const void* x, int32_t dtype, const bk_series_layout* layo
 /* per-series mean and ddof=1 variance (rhat.py:165-166); outputs [n_series] f64 */
 BK_API int bk_chain_moments(const void* x, int32_t dtype, const bk_series_layout* layout,
                             double* mean_out, double* var_out, void* stream);
+/* Streaming moments: fold a batch of draws [n_draws, n_elems] (the samplers'
+ * [n, C, D] output, n_elems = C * D) into running per-element mean / M2 (sum of
+ * squared deviations) that already cover n0 draws (n0 = 0 initialises them).
+ * var(ddof=1) = M2 / (n0 + n_draws - 1): R-hat (rhat.py:165-170) then needs no
+ * pass over the stored chains -- bk_rhat_from_moments on the result. */
+BK_API int bk_moments_accumulate(const void* draws, int32_t dtype, int64_t n_draws, int64_t n_elems,
+                          int64_t n0, double* mean_inout, double* m2_inout, void* stream);
 /* rhat (rhat.py:111-171) from per-chain moments laid out [n_chains, n_params];
  * lengths [n_chains] (ragged allowed) or NULL with common length N.
  * out [n_params] f64 */

@@ -190,3 +190,45 @@ def test_rank_sort_large_and_ties(bk):
         xt = torch.as_tensor(x, dtype=dt, device="cuda")
         want = od_rank(np_(xt).astype(np.float64))
         assert np.array_equal(np_(bk.rank_chains(xt)), want)
+
+
+@pytest.mark.parametrize("kind", ["hmc_iso", "hmc_dense", "mala_diag", "drghmc"])
+def test_streaming_moments_match_rhat_on_stored_draws(bk, kind):
+    """running per-chain moments folded batch by batch give the same R-hat
+    (rhat.py:111-171) as the kernel that reads the stored [draws, chains, params] array."""
+    from oracle.models import DensePrecGauss
+    if kind == "hmc_iso":
+        s = bk.HMCDiag(bk.IsoGauss(30), 0.3, 4, chains=64, seed=1)
+    elif kind == "hmc_dense":
+        s = bk.HMCDiag(bk.DensePrecGauss(DensePrecGauss.c2_precision(128, 1)), 0.1, 3, chains=300, seed=2)
+    elif kind == "mala_diag":
+        rng = np.random.default_rng(0)
+        s = bk.MALA(bk.DiagGauss(rng.normal(size=17), rng.uniform(0.5, 2, 17)), 0.05, chains=33, seed=3)
+    else:
+        s = bk.DrGhmcDiag(bk.IsoGauss(12), 2, [0.4, 0.2], [3, 6], 0.5, chains=40, seed=4)
+    kept = []
+    for n in (5, 1, 23, 40):
+        d, _ = s.sample_n(n, moments=True)
+        kept.append(d)
+    s.sample_n(7)                                              # not monitored
+    _, lp = s.sample_n(20, keep_draws=False, moments=True)     # monitored, draws not returned
+    assert lp.shape[0] == 20
+    mean, var, n = s.running_moments()
+    assert n == 5 + 1 + 23 + 40 + 20
+    allx = torch.cat(kept)                                     # the first 69 monitored draws
+    m_ref = allx.double().mean(0)
+    # R-hat from moments of exactly the stored draws: re-accumulate them through the ABI in odd batches
+    from bayes_kit_b200 import _lib as L
+    C_, D = allx.shape[1], allx.shape[2]
+    mu = torch.empty(C_, D, dtype=torch.float64, device="cuda"); m2 = torch.empty_like(mu)
+    n0 = 0
+    for a, b in ((0, 3), (3, 50), (50, 69)):
+        chunk = allx[a:b].contiguous()
+        L.check(L.lib().bk_moments_accumulate(chunk.data_ptr(), L.BK_F32, b - a, C_ * D, n0, mu.data_ptr(),
+                                              m2.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        n0 += b - a
+    np.testing.assert_allclose(np_(mu), np_(m_ref), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(np_(m2 / 68), np_(allx.double().var(0, unbiased=True)), rtol=1e-10)
+    from bayes_kit_b200.rhat import _rhat_from
+    np.testing.assert_allclose(np_(_rhat_from(mu, m2 / 68, None, 69)), np_(bk.rhat(allx, draws_first=True)), **TOL)
+    assert torch.isfinite(s.running_rhat()).all()
