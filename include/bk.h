@@ -223,6 +223,21 @@ BK_API int bk_smc_resample_indices_dev(const void* logw, int64_t M, int32_t dtyp
 BK_API int bk_gather_rows(const void* src, const int64_t* idx, int64_t M, int64_t D, int32_t dtype,
                    void* out, void* stream);
 
+/* ---- Stretcher: affine-invariant ensemble sampler (ensemble.py:9-66, the
+ * Goodman & Weare stretch move sketched in the reference's comments) --------
+ * One call moves the n_active walkers `active` [n_active, D] (in/out, with
+ * their cached log densities lp_active; *lp_valid_host = 0 re-evaluates them)
+ * against the complementary half `other` [n_other, D]:
+ *   j = floor(u0 * n_other);  z = (1/sqrt(a) + (sqrt(a) - 1/sqrt(a)) u1)^2
+ *   theta* = other[j] + z (theta_k - other[j])
+ *   accept iff log(u2) < (D - 1) log z + log p(theta*) - log p(theta_k)
+ * u0..u2: Philox keyed by (seed, chain_offset + k, draw_offset) or INJECTED
+ * uniforms [n_active, 3].  accept_out [n_active] or NULL. */
+BK_API size_t bk_stretch_workspace_bytes(uint64_t handle, int64_t n_active);
+BK_API int bk_stretch_move(uint64_t handle, void* active, void* lp_active, int32_t* lp_valid_host,
+                    const void* other, int64_t n_active, int64_t n_other, double a,
+                    const bk_rng* rng, int32_t* accept_out, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- diagnostics -------------------------------------------------------- */
 /* Where the draws of series s live: element t of series s is
  *   x[(s / n_inner) * outer_stride + (s % n_inner) * inner_stride + t * draw_stride]

@@ -373,3 +373,51 @@ def drghmc_batch(model, theta0, rho0, normals, uniforms, max_proposals,
                   prob_retry) for c in range(C)]
     return (np.stack([o[0] for o in out], 1), np.stack([o[1] for o in out], 1),
             np.stack([o[2] for o in out], 0), np.stack([o[3] for o in out], 1))
+
+
+# ---- Stretcher (ensemble.py:9-66) -- PARITY UNPINNED --------------------------------
+# Upstream the whole implementation is commented out, so there is no executable
+# reference: this is a restatement of the algorithm its comments sketch (Goodman &
+# Weare 2010), with the three uniforms of a move injected so the device kernel can be
+# compared draw for draw.  Conventions fixed here (the sketch leaves them open):
+# partner j = floor(u0 * m); z = (1/sqrt(a) + (sqrt(a) - 1/sqrt(a)) * u1) ** 2
+# (ensemble.py:43-46); accept iff log(u2) < (D-1) log z + lp(theta*) - lp(theta_k) (:48-53).
+def stretch_half(model, active, other, u, a=2.0):
+    """Move every walker of `active` [n, D] against `other` [m, D]; u [n, 3].
+    Returns (new_active, accepted [n] bool, logp of the new walkers)."""
+    active = np.array(active, dtype=np.float64, copy=True)
+    other = np.asarray(other, dtype=np.float64)
+    n, D = active.shape
+    m = other.shape[0]
+    lo, hi = 1.0 / np.sqrt(a), np.sqrt(a)
+    acc = np.zeros(n, dtype=bool)
+    lps = np.zeros(n)
+    for k in range(n):
+        j = min(int(u[k, 0] * m), m - 1)
+        z = np.square(lo + (hi - lo) * u[k, 1])
+        star = other[j] + z * (active[k] - other[j])
+        lp_k, lp_s = model.log_density(active[k]), model.log_density(star)
+        log_q = (D - 1) * np.log(z) + lp_s - lp_k
+        if _log_u(u[k, 2]) < log_q:
+            active[k], acc[k], lps[k] = star, True, lp_s
+        else:
+            lps[k] = lp_k
+    return active, acc, lps
+
+
+def stretch(model, thetas0, us, a=2.0):
+    """n_steps of Stretcher.sample() (ensemble.py:55-63): first half against the second,
+    then the second half against the UPDATED first.  us [n_steps, W, 3] (row k of a step
+    belongs to walker k).  Returns (thetas [n_steps, W, D], accepts [n_steps, W])."""
+    th = np.array(thetas0, dtype=np.float64, copy=True)
+    W = th.shape[0]
+    h = W // 2
+    out, accs = [], []
+    for u in us:
+        a1, acc1, _ = stretch_half(model, th[:h], th[h:], u[:h], a)
+        th[:h] = a1
+        a2, acc2, _ = stretch_half(model, th[h:], th[:h], u[h:], a)
+        th[h:] = a2
+        out.append(th.copy())
+        accs.append(np.concatenate([acc1, acc2]))
+    return np.stack(out), np.stack(accs)

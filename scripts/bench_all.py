@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bayes_kit_b200 as bk
 HBM = 6548.5  # GB/s measured (MEASURED_PEAKS.json)
-which = sys.argv[1:] or ["c1", "c1mala", "c2mala", "c3", "drghmc", "c4", "c5", "acf", "rnrhat"]
+which = sys.argv[1:] or ["c1", "c1mala", "c2mala", "c3", "drghmc", "c4", "c5", "acf", "rnrhat", "stretch"]
 
 def timed(fn, reps=5, warm=2):
     for _ in range(warm): fn()
@@ -134,3 +134,11 @@ if "rnrhat" in which:
     print(json.dumps({"workload": f"rank_normalized_rhat {Cn} chains x {N} draws x {P} params fp32 (radix sort of {N*Cn/1e6:.0f} M keys per parameter)",
           "ms": ms, "M_draws_per_s": n / (ms * 1e-3) / 1e6, "GBps_sort_traffic(80B/key)": n * 80 / 1e9 / (ms * 1e-3),
           "split_rhat_ms": ms_s, "split_rhat_GBps": n * 4 / 1e9 / (ms_s * 1e-3), "value": [float(v) for v in r]}), flush=True)
+
+if "stretch" in which:
+    from oracle.models import DensePrecGauss
+    D, W = 1000, 65536
+    s = bk.Stretcher(bk.DensePrecGauss(DensePrecGauss.c2_precision(D, 0)), walkers=W, seed=0)
+    ms = timed(lambda: s.sample(), reps=10, warm=3)
+    print(json.dumps({"workload": f"Stretcher (stretch move) {W} walkers x {D}-dim dense Gaussian fp32, one sweep",
+          "ms_per_sweep": ms, "walker_moves_per_s": W / (ms * 1e-3), "accept": float(s.last_accept.float().mean())}), flush=True)

@@ -2,7 +2,8 @@
  (1) sharded HMC == the same chains of a single-GPU run (Philox keyed by global chain id);
  (2) sharded TemperedLikelihoodSMC (multinomial, injected streams) reproduces the oracle's
      resample indices / particles exactly -- all-gather of log-weights + particles;
- (3) cross-chain R-hat from sharded chains == oracle on all chains."""
+ (3) cross-chain R-hat from sharded chains == oracle on all chains;
+ (4) sharded Stretcher (complementary-walker all-gather) == the oracle's single ensemble."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
@@ -46,6 +47,19 @@ ch = rng.normal(size=(12, 200, 3)) + rng.normal(size=(12, 1, 3))
 lo, hi = bd.shard_range(12, rank, world)
 r = bk.rhat(torch.as_tensor(ch[lo:hi], device=dev))
 assert np.allclose(np_(r), od.rhat_batch(ch), rtol=1e-12)
+# (4) Stretcher: walkers of both halves sharded, complementary half all-gathered per half-step
+D, W, n = 5, 24, 4
+om4 = __import__("oracle.models", fromlist=["IsoGauss"]).IsoGauss(D, 1.3)
+th0 = rng.normal(size=(W, D)); us = rng.random((n, W, 3))
+want, wacc = osm.stretch(om4, th0, us, a=2.0)
+st_ = bk.Stretcher(bk.IsoGauss(D, 1.3, dtype=torch.float64, device=dev), a=2.0, walkers=W, init=th0)
+h = W // 2
+lo, hi = bd.shard_range(h, rank, world)
+rows = np.r_[lo:hi, h + lo:h + hi]                      # this rank's walkers: its slice of each half
+for t in range(n):
+    got = st_.sample(uniforms=us[t][rows])
+    assert np.allclose(np_(got), want[t][rows], rtol=1e-10, atol=1e-10), ("stretcher", t)
+    assert np.array_equal(np_(st_.last_accept).astype(bool), wacc[t][rows])
 dist.barrier()
 if rank == 0:
     print(f"dist_check ok on {world} GPUs")
