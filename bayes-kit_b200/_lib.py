@@ -76,6 +76,8 @@ _SIGNATURES = {
     "bk_stretch_move": (C.c_int, [u64, vp, vp, C.POINTER(i32), vp, i64, i64, f64, C.POINTER(Rng), vp, vp, sz, vp]),
     "bk_smc_move_weight": (C.c_int, [u64, vp, i64, i32, i32, f64, C.POINTER(Rng), vp, vp, vp]),
     "bk_smc_gather_move_weight": (C.c_int, [u64, vp, vp, vp, i64, i32, i32, f64, C.POINTER(Rng), vp, vp, vp]),
+    "bk_smc_gather_move_weight_acc": (C.c_int, [u64, vp, vp, vp, i64, i32, i32, f64, C.POINTER(Rng), vp, vp, vp, vp]),
+    "bk_smc_adaptive_select": (C.c_int, [vp, f64, i64, i64, vp, vp, i32, vp, vp]),
     "bk_smc_resample_workspace_bytes": (sz, [i64]),
     "bk_smc_weight_stats": (C.c_int, [vp, i64, i32, i32, vp, vp, sz, vp]),
     "bk_smc_resample_indices": (C.c_int, [vp, i64, i32, i32, f64, f64, vp, C.POINTER(Rng), i64, i64,

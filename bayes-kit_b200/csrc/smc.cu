@@ -21,6 +21,7 @@ struct SmcArgs {
     T t0, t1, scale;
     bk_rng rng;
     T* logw;
+    const T* logw_prev;        // [M] log-weights carried from temperatures without resampling, or NULL
     int32_t* accept;
 };
 
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(128) k_smc_move_weight(SmcArgs<T> a) {
         if (active) {
             ln.store(a.thetas + m * (int64_t)a.D, th);
             if (ln.lane == 0) {
-                a.logw[m] = lw;
+                a.logw[m] = a.logw_prev ? A::add(a.logw_prev[m], lw) : lw;
                 if (a.accept) a.accept[m] = acc ? 1 : 0;
             }
         }
@@ -130,8 +131,8 @@ static int launch_smc(const SmcArgs<T>& a, cudaStream_t st) {
 
 template <typename T>
 static int smc_move_t(const Model& m, const void* src, const int64_t* src_idx, void* thetas, int64_t M,
-                      int n, int Tn, double scale, const bk_rng* rng, void* logw, int32_t* accept,
-                      cudaStream_t st) {
+                      int n, int Tn, double scale, const bk_rng* rng, void* logw, const void* logw_prev,
+                      int32_t* accept, cudaStream_t st) {
     SmcArgs<T> a;
     memset(&a, 0, sizeof(a));
     a.thetas = (T*)thetas;
@@ -145,6 +146,7 @@ static int smc_move_t(const Model& m, const void* src, const int64_t* src_idx, v
     a.scale = (T)scale;
     a.rng = *rng;
     a.logw = (T*)logw;
+    a.logw_prev = (const T*)logw_prev;
     a.accept = accept;
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     a.vec = (a.D % 4 == 0 && al(thetas) && al(src) && al(a.mu) && al(a.pl) && al(a.m0) && al(a.p0) &&
@@ -352,6 +354,20 @@ __global__ void k_gather(const T* __restrict__ src, const int64_t* __restrict__ 
     for (int e = lane; e < D; e += 32) o[e] = s[e];
 }
 
+// Adaptive resampling: resample only when the importance-weight ESS (sum w)^2 / sum w^2 falls below
+// the threshold; otherwise the particles stay (identity indices) and keep their log-weights.  The
+// decision is taken on device from the stats bk_smc_weight_stats wrote -- no host round trip.
+template <typename T>
+__global__ void k_smc_adaptive_select(const double* __restrict__ stats, double thr, int64_t n, int64_t point_offset,
+                                      int64_t* __restrict__ idx, T* __restrict__ logw, int32_t* __restrict__ flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool resample = stats[1] * stats[1] / stats[2] < thr;
+    if (i == 0 && flag) *flag = resample ? 1 : 0;
+    if (i >= n) return;
+    if (resample) logw[i] = T(0);            // equal weights after resampling
+    else idx[i] = point_offset + i;          // keep particle i and its accumulated log-weight
+}
+
 static int stat_blocks(int64_t M) {
     int64_t b = (M + RED_THREADS - 1) / RED_THREADS;
     return (int)(b < 1 ? 1 : (b > 1184 ? 1184 : b));  // 8 x 148 SMs
@@ -372,6 +388,13 @@ int bk_smc_move_weight(uint64_t handle, void* thetas, int64_t M, int32_t n, int3
 int bk_smc_gather_move_weight(uint64_t handle, const void* src, const int64_t* src_idx, void* thetas,
                               int64_t M, int32_t n, int32_t T, double scale, const bk_rng* rng,
                               void* logw_out, int32_t* accept_out, void* stream) {
+    return bk_smc_gather_move_weight_acc(handle, src, src_idx, thetas, M, n, T, scale, rng, nullptr, logw_out,
+                                         accept_out, stream);
+}
+
+int bk_smc_gather_move_weight_acc(uint64_t handle, const void* src, const int64_t* src_idx, void* thetas,
+                                  int64_t M, int32_t n, int32_t T, double scale, const bk_rng* rng,
+                                  const void* logw_prev, void* logw_out, int32_t* accept_out, void* stream) {
     const Model* m = get_model(handle);
     if (!m) return BK_E_HANDLE;
     BK_CHECK_ARG(m->d.kind == BK_MODEL_GAUSS_PRIOR_LIK,
@@ -384,9 +407,9 @@ int bk_smc_gather_move_weight(uint64_t handle, const void* src, const int64_t* s
                  "bk_smc_move_weight: injected rng needs normals/uniforms");
     if (M == 0) return BK_OK;
     if (m->d.dtype == BK_F64)
-        return smc_move_t<double>(*m, src, src_idx, thetas, M, n, T, scale, rng, logw_out, accept_out,
+        return smc_move_t<double>(*m, src, src_idx, thetas, M, n, T, scale, rng, logw_out, logw_prev, accept_out,
                                   (cudaStream_t)stream);
-    return smc_move_t<float>(*m, src, src_idx, thetas, M, n, T, scale, rng, logw_out, accept_out,
+    return smc_move_t<float>(*m, src, src_idx, thetas, M, n, T, scale, rng, logw_out, logw_prev, accept_out,
                              (cudaStream_t)stream);
 }
 
@@ -483,6 +506,20 @@ int bk_smc_resample_indices_dev(const void* logw, int64_t M, int32_t dtype, int3
     BK_CHECK_ARG(stats, "bk_smc_resample_indices_dev: stats is required");
     return resample_impl(logw, M, dtype, mode, 0.0, 1.0, stats, uniforms, rng, n_points, point_offset, idx_out,
                          cdf_out, ws, ws_bytes, stream);
+}
+
+int bk_smc_adaptive_select(const double* stats, double ess_threshold, int64_t n_points, int64_t point_offset,
+                           int64_t* idx_inout, void* logw_inout, int32_t dtype, int32_t* resampled_out, void* stream) {
+    BK_CHECK_ARG(stats && idx_inout && logw_inout && n_points >= 0, "bk_smc_adaptive_select: bad argument");
+    const unsigned blocks = (unsigned)((n_points + 255) / 256 > 0 ? (n_points + 255) / 256 : 1);
+    if (dtype == BK_F64)
+        k_smc_adaptive_select<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(stats, ess_threshold, n_points, point_offset,
+                                                                               idx_inout, (double*)logw_inout, resampled_out);
+    else
+        k_smc_adaptive_select<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(stats, ess_threshold, n_points, point_offset,
+                                                                              idx_inout, (float*)logw_inout, resampled_out);
+    BK_LAUNCH_CHECK();
+    return BK_OK;
 }
 
 int bk_gather_rows(const void* src, const int64_t* idx, int64_t M, int64_t D, int32_t dtype, void* out,

@@ -46,12 +46,16 @@ class TemperedLikelihoodSMC:
     * ``resample``: ``"multinomial"`` (reference semantics: no max-shift, legacy
       ``np.random.choice`` indices) or ``"systematic"`` (log-sum-exp normalised,
       stratified points; north_star item 2).
+    * ``ess_threshold``: None (the reference: resample at every temperature,
+      smc.py:60) or a fraction in (0, 1]: resample only when the importance-weight
+      ESS drops below ``ess_threshold * M``, carrying the log-weights otherwise
+      (``log_weights``, ``resampled``); the decision is taken on device.
     With torch.distributed initialised, M is the GLOBAL particle count and each
     rank owns a contiguous slice.
     """
 
     def __init__(self, model, M: int, N: int, sample_initial, kernel, *, resample: str = "multinomial",
-                 seed=None, group=None):
+                 ess_threshold: Optional[float] = None, seed=None, group=None):
         self._model = require_plugin(model)
         if not isinstance(self._model, GaussPriorLik):
             raise TypeError("TemperedLikelihoodSMC needs a model plugin with log_prior/log_likelihood "
@@ -61,6 +65,9 @@ class TemperedLikelihoodSMC:
                             "kernels cannot run per particle on the GPU and there is no CPU fallback")
         if resample not in ("multinomial", "systematic"):
             raise ValueError("resample must be 'multinomial' or 'systematic'")
+        if ess_threshold is not None and not 0 < ess_threshold <= 1:
+            raise ValueError(f"ess_threshold must be in (0, 1], got {ess_threshold}")
+        self.ess_threshold = ess_threshold      # None: resample at every temperature (smc.py:60)
         self.M, self.N = int(M), int(N)
         self.kernel = kernel
         self.resample = resample
@@ -86,6 +93,8 @@ class TemperedLikelihoodSMC:
         self.last_indices = None
         self.last_accept = None
         self._stats_log = []  # per temperature: device tensor [shift, sum w, sum w^2]
+        self._logw_acc = None  # adaptive resampling: log-weights carried between temperatures
+        self._resampled_log = []
 
     # ---- reference surface -----------------------------------------------------------
     @property
@@ -133,6 +142,20 @@ class TemperedLikelihoodSMC:
         s = torch.stack(self._stats_log).cpu()
         return [float(a * a / b) if b > 0 else float("nan") for _, a, b in s.tolist()]
 
+    @property
+    def log_weights(self) -> torch.Tensor:
+        """Unnormalised log-weights of the current particles (zeros right after a resampling)."""
+        if self._logw_acc is None:
+            return torch.zeros(self._hi - self._lo, dtype=self.dtype, device=self.device)
+        return self._logw_acc
+
+    @property
+    def resampled(self):
+        """Per temperature taken so far: did the adaptive rule resample?"""
+        if not self._resampled_log:
+            return []
+        return [bool(v) for v in torch.cat(self._resampled_log).cpu().tolist()]
+
     def transition(self, n: int, normals=None, acc_uniforms=None, res_uniforms=None) -> None:
         """One temperature step (smc.py:46-60).  The optional arrays inject the
         reference's recorded legacy-RNG streams (parity mode): proposal normals
@@ -148,17 +171,18 @@ class TemperedLikelihoodSMC:
         rng = make_rng(self._seed, n, self._lo, normals, acc_uniforms, 1)
         mode = L.RESAMPLE_MULTINOMIAL if self.resample == "multinomial" else L.RESAMPLE_SYSTEMATIC
         with torch.cuda.device(self.device):
+            prev = None if self._logw_acc is None else self._logw_acc.data_ptr()
             if self._pending is not None:     # move reads thetas_prev[idx]: gather + move in one pass
                 src, src_idx = self._pending
                 moved = torch.empty(Ml, self.D, dtype=self.dtype, device=self.device)
-                L.check(lib.bk_smc_gather_move_weight(
+                L.check(lib.bk_smc_gather_move_weight_acc(
                     self._model.handle, src.data_ptr(), src_idx.data_ptr(), moved.data_ptr(), Ml, n, self.N,
-                    self.kernel.scale, C.byref(rng), logw.data_ptr(), acc.data_ptr(), st))
+                    self.kernel.scale, C.byref(rng), prev, logw.data_ptr(), acc.data_ptr(), st))
                 self._thetas, self._pending = moved, None
             else:
-                L.check(lib.bk_smc_move_weight(self._model.handle, self._thetas.data_ptr(), Ml, n, self.N,
-                                               self.kernel.scale, C.byref(rng), logw.data_ptr(),
-                                               acc.data_ptr(), st))
+                L.check(lib.bk_smc_gather_move_weight_acc(
+                    self._model.handle, self._thetas.data_ptr(), None, self._thetas.data_ptr(), Ml, n, self.N,
+                    self.kernel.scale, C.byref(rng), prev, logw.data_ptr(), acc.data_ptr(), st))
             # --- the naturally global step: normaliser + resampling ---------------------
             logw_all = D_.all_gather_cat(logw, self._group)      # [M]
             thetas_all = D_.all_gather_cat(self._thetas, self._group)  # [M, D]
@@ -179,6 +203,13 @@ class TemperedLikelihoodSMC:
             L.check(lib.bk_smc_resample_indices_dev(
                 logw_all.data_ptr(), Mg, L.BK_F32 if self.dtype == torch.float32 else L.BK_F64, mode,
                 stats.data_ptr(), ptr(ru), C.byref(rrng), Ml, self._lo, idx.data_ptr(), None, wp, wn, st))
+            if self.ess_threshold is not None:
+                flag = torch.empty(1, dtype=torch.int32, device=self.device)
+                L.check(lib.bk_smc_adaptive_select(
+                    stats.data_ptr(), float(self.ess_threshold) * Mg, Ml, self._lo, idx.data_ptr(), logw.data_ptr(),
+                    L.BK_F32 if self.dtype == torch.float32 else L.BK_F64, flag.data_ptr(), st))
+                self._logw_acc = logw
+                self._resampled_log.append(flag)
         self._pending = (thetas_all, idx)     # thetas[idxs]: folded into the next move (or .thetas)
         self.last_indices = idx
         self.last_accept = acc

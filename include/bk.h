@@ -192,6 +192,22 @@ BK_API int bk_smc_move_weight(uint64_t handle, void* thetas, int64_t M, int32_t 
 BK_API int bk_smc_gather_move_weight(uint64_t handle, const void* src, const int64_t* src_idx,
                        void* thetas, int64_t M, int32_t n, int32_t T, double scale,
                        const bk_rng* rng, void* logw_out, int32_t* accept_out, void* stream);
+/* ... and with log-weights carried over from temperatures that did not resample
+ * (adaptive resampling): logw_out[m] = logw_prev[m] + (lp_n - lp_{n-1}); logw_prev
+ * NULL = the call above. */
+BK_API int bk_smc_gather_move_weight_acc(uint64_t handle, const void* src, const int64_t* src_idx,
+                       void* thetas, int64_t M, int32_t n, int32_t T, double scale,
+                       const bk_rng* rng, const void* logw_prev, void* logw_out,
+                       int32_t* accept_out, void* stream);
+/* Adaptive resampling (the reference resamples unconditionally,
+ * smc.py:60): after bk_smc_weight_stats and bk_smc_resample_indices, keep the
+ * computed indices and zero the log-weights iff (sum w)^2 / sum w^2 <
+ * ess_threshold, else overwrite idx with the identity (point_offset + i) and keep
+ * the accumulated log-weights.  Decided on device from `stats`; *resampled_out
+ * (device int32, may be NULL) records the decision. */
+BK_API int bk_smc_adaptive_select(const double* stats, double ess_threshold, int64_t n_points,
+                       int64_t point_offset, int64_t* idx_inout, void* logw_inout, int32_t dtype,
+                       int32_t* resampled_out, void* stream);
 BK_API size_t bk_smc_resample_workspace_bytes(int64_t M);
 /* local reduction of the log-weights: stats_out[0] = max, [1] = sum exp(logw -
  * shift), [2] = sum exp(..)^2 where shift = max (SYSTEMATIC) or 0

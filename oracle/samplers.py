@@ -421,3 +421,28 @@ def stretch(model, thetas0, us, a=2.0):
         out.append(th.copy())
         accs.append(np.concatenate([acc1, acc2]))
     return np.stack(out), np.stack(accs)
+
+
+def smc_tempered_adaptive(model, thetas0, prop_normals, acc_uniforms, res_uniforms, scale, T, ess_threshold):
+    """TemperedLikelihoodSMC with ESS-triggered systematic resampling -- PARITY UNPINNED (the
+    reference resamples unconditionally, smc.py:60; this is the textbook adaptive variant).
+    Moves as in smc_tempered; log-weights accumulate until (sum w)^2 / sum w^2 < ess_threshold * M,
+    then systematic resampling with u0 = res_uniforms[n-1, 0] and the weights reset.
+    Returns (thetas, logw, resampled [T] bool)."""
+    thetas = np.array(thetas0, dtype=np.float64, copy=True)
+    M = thetas.shape[0]
+    logw = np.zeros(M)
+    flags = np.zeros(T, dtype=bool)
+    for n in range(1, T + 1):
+        t0, t1 = (n - 1) / T, n / T
+        lp = lambda th, t: model.log_likelihood(th) * t + model.log_prior(th)
+        for m in range(M):
+            star = thetas[m] + scale * prop_normals[n - 1, m]
+            if _log_u(acc_uniforms[n - 1, m]) < lp(star, t0) - lp(thetas[m], t0):
+                thetas[m] = star
+        logw = logw + np.array([lp(th, t1) - lp(th, t0) for th in thetas])
+        w = np.exp(logw - logw.max())
+        if w.sum() ** 2 / (w ** 2).sum() < ess_threshold * M:
+            idx, _ = systematic_indices(logw, res_uniforms[n - 1, 0])
+            thetas, logw, flags[n - 1] = thetas[idx], np.zeros(M), True
+    return thetas, logw, flags

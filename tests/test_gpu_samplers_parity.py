@@ -160,6 +160,32 @@ def test_smc_systematic_vs_oracle(bk):
     np.testing.assert_allclose(np_(smc.thetas), oth, rtol=1e-12, atol=1e-12)
 
 
+@pytest.mark.parametrize("thr", [0.5, 0.9, 1.0])
+def test_smc_adaptive_resampling_vs_oracle(bk, thr):
+    """ESS-triggered resampling (parity unpinned upstream): the device decision, the carried
+    log-weights and the particles follow the oracle restatement under injected streams."""
+    from oracle.models import GaussPriorLik
+    rng = np.random.default_rng(11)
+    D, M, T, scale = 5, 300, 12, 0.3
+    mu = rng.normal(size=D)
+    om = GaussPriorLik(np.zeros(D), np.ones(D), mu, 4 * np.ones(D))
+    th0 = rng.normal(size=(M, D))
+    zs, au, ru = rng.standard_normal((T, M, D)), rng.random((T, M)), rng.random((T, M))
+    oth, ologw, oflags = osm.smc_tempered_adaptive(om, th0, zs, au, ru, scale, T, thr)
+    model = bk.GaussPriorLik(np.zeros(D), np.ones(D), mu, 4 * np.ones(D), dtype=torch.float64)
+    smc = bk.TemperedLikelihoodSMC(model, M, T, th0, bk.metropolis_kernel(scale), resample="systematic",
+                                   ess_threshold=thr)
+    for n in range(1, T + 1):
+        smc.transition(n, normals=zs[n - 1], acc_uniforms=au[n - 1], res_uniforms=ru[n - 1, :1])
+    assert smc.resampled == list(oflags)
+    if thr < 1.0:
+        assert 0 < sum(oflags) < T           # the rule actually skips some temperatures
+    np.testing.assert_allclose(np_(smc.thetas), oth, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(np_(smc.log_weights), ologw, rtol=1e-10, atol=1e-12)
+    with pytest.raises(ValueError):
+        bk.TemperedLikelihoodSMC(model, M, T, th0, bk.metropolis_kernel(scale), ess_threshold=1.5)
+
+
 def test_model_protocol(bk):
     """dims / log_density / log_density_gradient of every plugin vs the numpy models."""
     from oracle import models as om
