@@ -191,6 +191,33 @@ __device__ __forceinline__ double philox_uniform<double>(uint64_t seed, uint32_t
     return (k & 1) ? u01d(r[2], r[3]) : u01d(r[0], r[1]);
 }
 
+// Accept uniform of the single-uniform samplers (HMC / MALA / RW-Metropolis) in Philox mode.
+// The fused register-resident kernels lay a chain out over sep_slots(D) blocks of 4 elements; when the
+// LAST block is pure padding (4 (slots - 1) >= D) its normal-stream Philox words are unused by the
+// proposal and serve as the accept uniform -- one counter-mode call per lane and draw instead of two.
+// Every engine follows the same rule (this function), so chains do not depend on which engine ran.
+__host__ __device__ __forceinline__ int sep_slots(int D) {
+    return D <= 4 ? 1 : D <= 16 ? 4 : D <= 32 ? 8 : D <= 64 ? 16 : D <= 128 ? 32 : D <= 256 ? 64 : D <= 512 ? 128 : 0;
+}
+__host__ __device__ __forceinline__ bool accept_uniform_from_spare_block(int D) {
+    const int s = sep_slots(D);
+    return s > 0 && 4 * (s - 1) >= D;
+}
+template <typename T>
+__device__ __forceinline__ T uniform_of_words(uint32_t w0, uint32_t w1) {
+    if constexpr (sizeof(T) == 4) return u01(w0);
+    else return u01d(w0, w1);
+}
+template <typename T>
+__device__ __forceinline__ T philox_accept_uniform(uint64_t seed, uint32_t chain, uint32_t draw, int D) {
+    if (accept_uniform_from_spare_block(D)) {
+        uint32_t r[4];
+        Philox::gen(seed, (uint32_t)(sep_slots(D) - 1), TAG_NORMAL, chain, draw, r);
+        return uniform_of_words<T>(r[0], r[1]);
+    }
+    return philox_uniform<T>(seed, 0u, chain, draw);
+}
+
 // ---- reductions over a group of G consecutive lanes (G power of two <= 32) ---
 template <int G, typename T>
 __device__ __forceinline__ T group_sum(T v) {

@@ -624,8 +624,8 @@ __global__ void __launch_bounds__(256) k_hmc_end_tc(HmcTcArgs p, int64_t t) {
     if (p.rng.mode == BK_RNG_INJECTED)
         u = reinterpret_cast<const float*>(p.rng.uniforms)[(t * p.C + c) * p.rng.n_uniform];
     else
-        u = philox_uniform<float>(p.rng.seed, 0u, (uint32_t)(p.rng.chain_offset + (uint64_t)c),
-                                  (uint32_t)(p.rng.draw_offset + (uint64_t)t));
+        u = philox_accept_uniform<float>(p.rng.seed, (uint32_t)(p.rng.chain_offset + (uint64_t)c),
+                                         (uint32_t)(p.rng.draw_offset + (uint64_t)t), D);
     const bool acc = log_u(u) < h1 - h0;
     float* dr = p.draws ? p.draws + (t * p.C + c) * (int64_t)D : nullptr;
 #pragma unroll 2

@@ -31,6 +31,9 @@ struct Row {
     __device__ __forceinline__ T uniform(int k) const {
         if (rng.mode == BK_RNG_INJECTED)
             return reinterpret_cast<const T*>(rng.uniforms)[(t * C + c) * rng.n_uniform + k];
+        if (k == 0 && rng.n_uniform == 1)      // the samplers' accept uniform: one rule for every engine
+            return philox_accept_uniform<T>(rng.seed, (uint32_t)(rng.chain_offset + (uint64_t)c),
+                                            (uint32_t)(rng.draw_offset + (uint64_t)t), D);
         return philox_uniform<T>(rng.seed, (uint32_t)k, (uint32_t)(rng.chain_offset + (uint64_t)c),
                                  (uint32_t)(rng.draw_offset + (uint64_t)t));
     }

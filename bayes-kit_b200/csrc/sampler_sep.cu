@@ -32,8 +32,18 @@ __global__ void __launch_bounds__(128) k_sep_sampler(SepArgs<T> a) {
 
     for (int64_t t = 0; t < a.n_draws; ++t) {
         T z[NE];
-        ln.normals(a.rng, a.C, chain, t, z);
-        const T logu = log_u(ln.uniform(a.rng, a.C, chain, t, 0));
+        uint32_t raw2[2] = {0u, 0u};
+        ln.normals(a.rng, a.C, chain, t, z, raw2);
+        // accept uniform (common.cuh: philox_accept_uniform): the padding block's words when there is one
+        T u;
+        if (a.rng.mode == BK_RNG_PHILOX && 4 * (G * J - 1) >= a.D) {
+            const uint32_t w0 = __shfl_sync(0xffffffffu, raw2[0], G - 1, G);
+            const uint32_t w1 = sizeof(T) == 8 ? __shfl_sync(0xffffffffu, raw2[1], G - 1, G) : 0u;
+            u = uniform_of_words<T>(w0, w1);
+        } else {
+            u = ln.uniform(a.rng, a.C, chain, t, 0);
+        }
+        const T logu = log_u(u);
         bool acc;
         T out_lp;
         if constexpr (ALGO == ALGO_HMC && MK == MK_ISO && sizeof(T) == 4) {

@@ -156,3 +156,24 @@ def test_smc_posterior(bk):  # test_tempered_smc.py:8-30 (Gaussian analogue)
         np.testing.assert_allclose(th.mean(0), 0.8 * mu, atol=0.05)
         np.testing.assert_allclose(th.var(0, ddof=1), 0.2 * np.ones(D), atol=0.05)
         assert len(smc.weight_ess) == T and all(1 <= e <= M + 1e-6 for e in smc.weight_ess)
+
+
+@pytest.mark.parametrize("D", [3, 12, 13, 100, 125, 200])
+def test_engines_agree_in_philox_mode(bk, D, monkeypatch):
+    """Device-RNG chains do not depend on which engine ran: the fused register-resident kernel and
+    the generic row kernels follow one rule for the accept uniform (spare Philox block or the
+    dedicated stream, common.cuh) and the same normal blocks."""
+    res = []
+    for force in ("0", "1"):
+        monkeypatch.setenv("BK_FORCE_GENERIC", force)
+        out = []
+        for mk in (lambda: bk.HMCDiag(bk.IsoGauss(D, dtype=torch.float64), 0.2, 3, chains=70, seed=5),
+                   lambda: bk.MALA(bk.IsoGauss(D, dtype=torch.float64), 0.05, chains=70, seed=6),
+                   lambda: bk.Metropolis(bk.IsoGauss(D, dtype=torch.float64), bk.GaussianRW(0.3), chains=70, seed=7)):
+            s = mk()
+            d, _ = s.sample_n(6)
+            out.append((np_(d), np_(s.last_accept)))
+        res.append(out)
+    for (d0, a0), (d1, a1) in zip(*res):
+        assert np.array_equal(a0, a1)
+        np.testing.assert_allclose(d0, d1, rtol=1e-12, atol=1e-12)
