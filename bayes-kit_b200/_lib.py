@@ -89,6 +89,7 @@ _SIGNATURES = {
     "bk_rank_normalize": (C.c_int, [vp, i32, C.POINTER(SeriesLayout), vp, vp, vp, sz, vp]),
     "bk_autocorr_workspace_bytes": (sz, [i64, i64]),
     "bk_autocorr": (C.c_int, [vp, i32, C.POINTER(SeriesLayout), vp, vp, sz, vp]),
+    "bk_iat_ess_workspace_bytes": (sz, [i32, C.POINTER(SeriesLayout)]),
     "bk_iat_ess": (C.c_int, [vp, i32, C.POINTER(SeriesLayout), i32, vp, vp, vp, sz, vp]),
     "bk_chain_moments": (C.c_int, [vp, i32, C.POINTER(SeriesLayout), vp, vp, vp]),
     "bk_moments_accumulate": (C.c_int, [vp, i32, i64, i64, i64, vp, vp, vp]),

@@ -267,6 +267,11 @@ static SeriesView view_of(const void* x, int32_t dtype, const bk_series_layout* 
 
 extern "C" {
 
+size_t bk_iat_ess_workspace_bytes(int32_t dtype, const bk_series_layout* layout) {
+    if (!layout) return 0;
+    return ess_stream_ws_bytes(view_of(nullptr, dtype, layout));
+}
+
 size_t bk_autocorr_workspace_bytes(int64_t n_series, int64_t N) {
     if (n_series <= 0 || N < 2) return 256;
     return acf_fft_ws_bytes(n_series, N);
@@ -357,7 +362,6 @@ int bk_autocorr(const void* x, int32_t dtype, const bk_series_layout* layout, do
 
 int bk_iat_ess(const void* x, int32_t dtype, const bk_series_layout* layout, int32_t estimator,
                double* iat_out, double* ess_out, void* ws, size_t ws_bytes, void* stream) {
-    (void)ws; (void)ws_bytes;
     int rc = check_series(x, dtype, layout, "bk_iat_ess");
     if (rc) return rc;
     BK_CHECK_ARG(layout->n_draws >= 4, "iat/ess require len(chain) >= 4, but len(chain)=%lld",
@@ -370,7 +374,8 @@ int bk_iat_ess(const void* x, int32_t dtype, const bk_series_layout* layout, int
     if (e && e[0] == 'b')
         return acf_launch(view_of(x, dtype, layout), 1, estimator, nullptr, iat_out, ess_out,
                           (cudaStream_t)stream);
-    return ess_stream_launch(view_of(x, dtype, layout), estimator, iat_out, ess_out, (cudaStream_t)stream);
+    return ess_stream_launch(view_of(x, dtype, layout), estimator, iat_out, ess_out, ws, ws_bytes,
+                             (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -17,7 +17,9 @@ struct SeriesView {
 
 
 // streaming Geyer IAT / ESS, one warp per series (ess_stream.cu)
-int ess_stream_launch(const SeriesView& v, int estimator, double* iat, double* ess, cudaStream_t st);
+size_t ess_stream_ws_bytes(const SeriesView& v);
+int ess_stream_launch(const SeriesView& v, int estimator, double* iat, double* ess, void* ws, size_t ws_bytes,
+                      cudaStream_t st);
 
 // hand-written FFT autocorrelation (fft_autocorr.cu)
 size_t acf_fft_ws_bytes(int64_t n_series, int64_t N);

@@ -205,7 +205,68 @@ __global__ void __launch_bounds__(ES_WARPS * 32, 2) k_ess_stream(SeriesView v, i
     }
 }
 
-int ess_stream_launch(const SeriesView& v, int estimator, double* iat, double* ess, cudaStream_t st) {
+// [series, draws] copy of a block of series whose draws are strided in memory (the samplers'
+// [draws, chains, params] layout: neighbouring series are neighbouring words, one series' draws are
+// a whole row apart).  32 x 32 tiles through shared memory: reads coalesced along the series axis,
+// writes along the draw axis.  A warp walking ONE such series would use 4 bytes of every 32-byte
+// sector it touches and a new page per draw.
+template <typename TI>
+__global__ void __launch_bounds__(256) k_gather_series(SeriesView v, int64_t s0, int64_t ns, TI* __restrict__ out) {
+    __shared__ TI tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t sb = (int64_t)blockIdx.x * 32, tb = (int64_t)blockIdx.y * 32;
+    const TI* x = reinterpret_cast<const TI*>(v.x);
+    {
+        const int64_t s = s0 + sb + tx;
+        if (sb + tx < ns) {
+            const int64_t base = (s / v.n_inner) * v.ostride + (s % v.n_inner) * v.istride;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int64_t t = tb + ty + 8 * k;
+                if (t < v.N) tile[ty + 8 * k][tx] = x[base + t * v.dstride];
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t sl = sb + ty + 8 * k, t = tb + tx;
+        if (sl < ns && t < v.N) out[sl * v.N + t] = tile[tx][ty + 8 * k];
+    }
+}
+
+size_t ess_stream_ws_bytes(const SeriesView& v) {
+    if (v.dstride == 1 || v.n_series == 0) return 0;
+    const size_t esz = v.dtype == BK_F64 ? 8 : 4;
+    const int64_t ns = v.n_series < 65536 ? v.n_series : 65536;
+    return (size_t)ns * v.N * esz + 256;
+}
+
+static int ess_stream_launch_direct(const SeriesView& v, int estimator, double* iat, double* ess, cudaStream_t st);
+
+// strided draws + scratch available: gather blocks of series into [series, draws] form first
+int ess_stream_launch(const SeriesView& v, int estimator, double* iat, double* ess, void* ws, size_t ws_bytes,
+                      cudaStream_t st) {
+    const size_t esz = v.dtype == BK_F64 ? 8 : 4;
+    const int64_t fit = ws ? (int64_t)((ws_bytes > 256 ? ws_bytes - 256 : 0) / ((size_t)v.N * esz)) : 0;
+    if (v.dstride == 1 || fit < 32 || v.n_series < 64) return ess_stream_launch_direct(v, estimator, iat, ess, st);
+    int64_t chunk = fit < v.n_series ? fit : v.n_series;
+    if (chunk < v.n_series) chunk = chunk / 32 * 32;       // full 32-series tiles except at the very end
+    void* buf = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    for (int64_t s0 = 0; s0 < v.n_series; s0 += chunk) {
+        const int64_t ns = v.n_series - s0 < chunk ? v.n_series - s0 : chunk;
+        dim3 grid((unsigned)((ns + 31) / 32), (unsigned)((v.N + 31) / 32));
+        if (v.dtype == BK_F64) k_gather_series<double><<<grid, 256, 0, st>>>(v, s0, ns, (double*)buf);
+        else k_gather_series<float><<<grid, 256, 0, st>>>(v, s0, ns, (float*)buf);
+        BK_LAUNCH_CHECK();
+        const SeriesView sv{buf, v.dtype, ns, v.N, 1, v.N, 0, 1};
+        int rc = ess_stream_launch_direct(sv, estimator, iat ? iat + s0 : nullptr, ess ? ess + s0 : nullptr, st);
+        if (rc) return rc;
+    }
+    return BK_OK;
+}
+
+static int ess_stream_launch_direct(const SeriesView& v, int estimator, double* iat, double* ess, cudaStream_t st) {
     // rings + 2 staging chunks per warp
     const size_t esz = v.dtype == BK_F64 ? 8 : 4;
     const size_t smem = (size_t)ES_WARPS * (ES_RING_DOUBLES * sizeof(double) + 2 * ES_CH * esz);

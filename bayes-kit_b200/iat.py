@@ -27,8 +27,10 @@ def _iat_ess(chain, estimator, device, draws_first, what):
         raise ValueError(f"{what} requires len(chain) >= 4, but len(chain)={lay.n_draws}")
     t = torch.empty(lay.n_series, dtype=torch.float64, device=x.device)
     e = torch.empty_like(t)
+    dt_ = L.BK_F32 if x.dtype == torch.float32 else L.BK_F64
     call(x, lambda lib, xp, dt, st, wp, wn: lib.bk_iat_ess(xp, dt, C.byref(lay), estimator, t.data_ptr(),
-                                                          e.data_ptr(), wp, wn, st))
+                                                          e.data_ptr(), wp, wn, st),
+         ws_bytes=L.lib().bk_iat_ess_workspace_bytes(dt_, C.byref(lay)))
     h = is_host(chain)
     return finish(t, res, h), finish(e, res, h)
 

@@ -280,6 +280,10 @@ BK_API size_t bk_autocorr_workspace_bytes(int64_t n_series, int64_t N);
  * out [n_series, N] f64 */
 BK_API int bk_autocorr(const void* x, int32_t dtype, const bk_series_layout* layout, double* out,
                        void* ws, size_t ws_bytes, void* stream);
+/* Scratch for bk_iat_ess: 0 when every series' draws are contiguous; otherwise room to gather
+ * blocks of up to 65,536 series into [series, draws] form (optional: without it the strided
+ * series are read in place, correct but sector-inefficient). */
+BK_API size_t bk_iat_ess_workspace_bytes(int32_t dtype, const bk_series_layout* layout);
 /* iat_ipse/iat_imse (iat.py:46-135) and ess_* (ess.py:5-69); outputs [n_series] f64 */
 BK_API int bk_iat_ess(const void* x, int32_t dtype, const bk_series_layout* layout, int32_t estimator,
                       double* iat_out, double* ess_out, void* ws, size_t ws_bytes, void* stream);

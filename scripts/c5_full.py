@@ -1,0 +1,59 @@
+"""BASELINE config c5 at FULL size: diagnostics on 8,192 chains x 10,000 draws x 100 params
+(32.8 GB of fp32 draws in the samplers' [draws, chains, params] layout, consumed in place).
+Correctness through size-independent properties: AR(1) series with known phi -> closed-form IAT
+(1 + phi) / (1 - phi) (test_iat.py:18-26), R-hat -> 1 for stationary chains, acf[0] = 1,
+acf[1] -> phi, ranks are a permutation.  One JSON line per diagnostic."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bayes_kit_b200 as bk
+
+N, Cn, P = 10000, int(os.environ.get("C5_CHAINS", "8192")), 100
+dev = "cuda"
+g = torch.Generator(device=dev); g.manual_seed(0)
+phi = torch.rand(Cn, P, device=dev, generator=g) * 0.9
+x = torch.empty(N, Cn, P, device=dev)
+cur = torch.randn(Cn, P, device=dev, generator=g) / torch.sqrt(1 - phi * phi)     # stationary start
+for t in range(N):
+    cur = phi * cur + torch.randn(Cn, P, device=dev, generator=g)
+    x[t] = cur
+torch.cuda.synchronize()
+
+def timed(fn):
+    fn()                                   # warm-up (first-call attribute setup, allocator)
+    torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); r = fn(); e1.record(); torch.cuda.synchronize()
+    return r, e0.elapsed_time(e1)
+
+S = Cn * P
+e, ms = timed(lambda: bk.ess(x, draws_first=True))
+iat_true = (1 + phi) / (1 - phi)
+rel = ((N / e) / iat_true - 1).abs()
+print(json.dumps({"diag": "ess", "series": S, "draws": N, "ms": ms, "series_per_s": S / ms * 1e3,
+                  "median_rel_err_vs_closed_form_IAT": float(rel.median()), "p99_rel_err": float(rel.flatten().kthvalue(int(0.99 * S)).values)}), flush=True)
+assert float(rel.median()) < 0.08
+r, ms = timed(lambda: bk.rhat(x, draws_first=True))
+print(json.dumps({"diag": "rhat", "params": P, "chains": Cn, "ms": ms, "GBps": S * N * 4 / 1e6 / ms,
+                  "max_abs_rhat_minus_1": float((r - 1).abs().max())}), flush=True)
+assert float((r - 1).abs().max()) < 5e-3
+r, ms = timed(lambda: bk.split_rhat(x, draws_first=True))
+print(json.dumps({"diag": "split_rhat", "ms": ms, "GBps": S * N * 4 / 1e6 / ms, "max_abs_minus_1": float((r - 1).abs().max())}), flush=True)
+assert float((r - 1).abs().max()) < 5e-3
+# rank-normalised R-hat: 81.9 M keys per parameter; 4 of the 100 parameters (each is an independent sort)
+xs = x[:, :, :4].contiguous()
+r, ms = timed(lambda: bk.rank_normalized_rhat(xs, draws_first=True))
+print(json.dumps({"diag": "rank_normalized_rhat", "params": 4, "keys_per_param": Cn * N, "ms": ms,
+                  "G_keys_per_s": 4 * Cn * N / ms / 1e6, "max_abs_minus_1": float((r - 1).abs().max())}), flush=True)
+assert float((r - 1).abs().max()) < 5e-3
+rk = bk.rank_chains(x[:, :256, 0].contiguous(), draws_first=True)          # [256, N] ranks: a permutation of 1..S
+assert torch.equal(rk.flatten().sort().values, torch.arange(1, 256 * N + 1, device=dev, dtype=torch.float64))
+del xs, rk
+# all-lag autocorrelation: every series of 10 parameters (81,920 series; the output is [series, N] fp64)
+xa = x[:, :, :10].permute(1, 2, 0).reshape(-1, N)            # view -> as_series makes it contiguous [series, draws]
+a, ms = timed(lambda: bk.autocorr(xa))
+ph = phi[:, :10].reshape(-1)
+print(json.dumps({"diag": "autocorr", "series": a.shape[0], "ms": ms, "series_per_s": a.shape[0] / ms * 1e3,
+                  "max_abs_acf0_minus_1": float((a[:, 0] - 1).abs().max()),
+                  "median_abs_acf1_minus_phi": float((a[:, 1] - ph.double()).abs().median())}), flush=True)
+assert float((a[:, 0] - 1).abs().max()) < 1e-9 and float((a[:, 1] - ph.double()).abs().median()) < 0.02
+print("c5 full size ok")
