@@ -486,7 +486,8 @@ size_t hlr_tc_eval_ws_bytes(const Model& m, int64_t C) {
 // mode: HLR_TC_GRAD (gradient partials only), HLR_TC_GRAD_LL (+ bf16-grade log-likelihood),
 //       HLR_TC_LP (split-precision log-likelihood only, part_g untouched)
 int hlr_tc_partial(const Model& m, const float* theta, int64_t C, void* ws, size_t ws_bytes, float** part_g,
-                   float** part_ll, int* n_split, cudaStream_t st, int mode) {
+                   float** part_ll, int* n_split, cudaStream_t st, int mode, bool operand_ready,
+                   __nv_bfloat16** operand) {
     const int D = (int)m.d.dims, Dx = D - 2;
     const int64_t N = m.d.n_obs, Np = pad128(N), Cp = pad128(C);
     const int ns = hlr_tc_splits(C, N);
@@ -496,11 +497,14 @@ int hlr_tc_partial(const Model& m, const float* theta, int64_t C, void* ws, size
     float* pg = ar.take<float>((size_t)ns * C * Dx);
     float* pl = ar.take<float>((size_t)ns * C);
     if (!ar.ok()) { set_error("model eval workspace too small (%zu < %zu)", ws_bytes, ar.off); return BK_E_WORKSPACE; }
-    // gradient-only mode folds the 1/2 of sigmoid(z) = 1/2 + tanh(z/2)/2 into the operand (exact in bf16)
-    k_hlr_prep_beta<<<(unsigned)((Cp * KJ + 255) / 256), 256, 0, st>>>(theta, C, Cp, Dx, D,
-                                                                       mode == HLR_TC_GRAD ? 0.5f : 1.0f, bb,
-                                                                       mode == HLR_TC_LP ? bl : nullptr);
-    BK_LAUNCH_CHECK();
+    if (operand) *operand = bb;
+    if (!operand_ready) {
+        // gradient-only mode folds the 1/2 of sigmoid(z) = 1/2 + tanh(z/2)/2 into the operand (exact in bf16)
+        k_hlr_prep_beta<<<(unsigned)((Cp * KJ + 255) / 256), 256, 0, st>>>(theta, C, Cp, Dx, D,
+                                                                           mode == HLR_TC_GRAD ? 0.5f : 1.0f, bb,
+                                                                           mode == HLR_TC_LP ? bl : nullptr);
+        BK_LAUNCH_CHECK();
+    }
     CUtensorMap mB, mBl, mX, mXl;
     int rc;
     if ((rc = make_map_bf16(&mB, bb, Cp, KJ, KJ, CT))) return rc;
@@ -530,6 +534,71 @@ int hlr_tc_partial(const Model& m, const float* theta, int64_t C, void* ws, size
     prof_end(BK_PROF_GRAD, st);
     BK_LAUNCH_CHECK();
     *part_g = pg; *part_ll = pl; *n_split = ns;
+    return BK_OK;
+}
+
+// ---- interior leapfrog step, fused around the tensor-core gradient ---------------------------
+// One warp per chain: fixed-order sum of the observation slices + hierarchical prior terms (the
+// gradient), the leapfrog kick and drift  r += eps m g ; q += eps r  (hmc.py:48-49), and the bf16
+// operand (beta / 2, zero padded) of the NEXT gradient launch -- instead of three kernels
+// (finish, step, operand preparation) and two round trips of the gradient through HBM.
+__global__ void k_hlr_finish_step(float* __restrict__ q, float* __restrict__ r, const float* __restrict__ part_g,
+                                  int64_t C, int Dx, int D, int n_split, float eps, const float* __restrict__ metric,
+                                  __nv_bfloat16* __restrict__ operand) {
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= C) return;
+    float* th = q + c * D;
+    float* rr = r + c * D;
+    const float mu = th[Dx], lam = th[Dx + 1];
+    const float e2 = expf(-2.f * lam), ep2 = expf(2.f * lam);
+    float sr = 0.f, ss = 0.f;
+    const int64_t step = C * (int64_t)Dx;
+    for (int j = lane; j < KJ; j += 32) {
+        float bq = 0.f;
+        if (j < Dx) {
+            const float d = th[j] - mu;
+            sr += d;
+            ss = fmaf(d, d, ss);
+            float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+            const float* pg = part_g + c * Dx + j;
+            int s = 0;
+            for (; s + 4 <= n_split; s += 4) {
+                const float a0 = pg[(s + 0) * step], a1 = pg[(s + 1) * step], a2 = pg[(s + 2) * step],
+                            a3 = pg[(s + 3) * step];
+                g0 += a0; g1 += a1; g2 += a2; g3 += a3;
+            }
+            for (; s < n_split; ++s) g0 += pg[s * step];
+            const float g = ((g0 + g1) + (g2 + g3)) - e2 * d;
+            const float rn = fmaf(eps * (metric ? metric[j] : 1.f), g, rr[j]);
+            rr[j] = rn;
+            bq = fmaf(eps, rn, th[j]);
+            th[j] = bq;
+        }
+        operand[c * KJ + j] = __float2bfloat16_rn(0.5f * bq);
+    }
+    sr = warp_sum(sr);
+    ss = warp_sum(ss);
+    if (lane == 0) {
+        const float gmu = e2 * sr - mu, glam = -(float)Dx + e2 * ss - ep2 + 1.f;
+        const float r0 = fmaf(eps * (metric ? metric[Dx] : 1.f), gmu, rr[Dx]);
+        const float r1 = fmaf(eps * (metric ? metric[Dx + 1] : 1.f), glam, rr[Dx + 1]);
+        rr[Dx] = r0; rr[Dx + 1] = r1;
+        th[Dx] = fmaf(eps, r0, mu);
+        th[Dx + 1] = fmaf(eps, r1, lam);
+    }
+}
+
+int hlr_tc_interior_step(const Model& m, float* q, float* r, int64_t C, float eps, const float* metric,
+                         bool operand_ready, void* ws, size_t ws_bytes, cudaStream_t st) {
+    float *pg, *pl;
+    int ns;
+    __nv_bfloat16* bb;
+    int rc = hlr_tc_partial(m, q, C, ws, ws_bytes, &pg, &pl, &ns, st, HLR_TC_GRAD, operand_ready, &bb);
+    if (rc) return rc;
+    const int D = (int)m.d.dims;
+    k_hlr_finish_step<<<(unsigned)((C * 32 + 63) / 64), 64, 0, st>>>(q, r, pg, C, D - 2, D, ns, eps, metric, bb);
+    BK_LAUNCH_CHECK();
     return BK_OK;
 }
 

@@ -46,6 +46,12 @@ bool hlr_tc_enabled(const Model& m);
 size_t hlr_tc_eval_ws_bytes(const Model& m, int64_t C);
 enum { HLR_TC_GRAD = 0, HLR_TC_GRAD_LL = 1, HLR_TC_LP = 2 };
 int hlr_tc_partial(const Model& m, const float* theta, int64_t C, void* ws, size_t ws_bytes, float** part_g,
-                   float** part_ll, int* n_split, cudaStream_t st, int mode);
+                   float** part_ll, int* n_split, cudaStream_t st, int mode, bool operand_ready = false,
+                   __nv_bfloat16** operand = nullptr);
+// interior leapfrog step of HMC on this plugin: tensor-core gradient of q, then ONE kernel that finishes
+// the gradient, applies kick + drift to (r, q) in place and writes the next launch's bf16 operand.
+// operand_ready: the operand of q was written by the previous call (same ws, same C).
+int hlr_tc_interior_step(const Model& m, float* q, float* r, int64_t C, float eps, const float* metric,
+                         bool operand_ready, void* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace bk

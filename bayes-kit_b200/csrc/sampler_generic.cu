@@ -291,7 +291,19 @@ int run_generic(const Model& m, GenArgs<T> p, int algo, int* cache_valid, void* 
         if (algo == ALGO_HMC) {
             k_hmc_begin<T><<<blocks, 256, 0, st>>>(p, t);
             BK_LAUNCH_CHECK();
+            bool operand_ready = false;
             for (int s = 0; s < p.L; ++s) {
+                if constexpr (sizeof(T) == 4) {
+                    // regression plugin, interior step: tensor-core gradient + ONE fused kernel
+                    // (gradient finish, kick, drift, next bf16 operand) -- logreg_tc.cu
+                    if (fast && m.d.kind == BK_MODEL_HIER_LOGREG && s + 1 < p.L) {
+                        rc = hlr_tc_interior_step(m, (float*)p.q, (float*)p.r, p.C, (float)p.eps,
+                                                  (const float*)p.metric, operand_ready, ews, ebytes, st);
+                        if (rc) return rc;
+                        operand_ready = true;
+                        continue;
+                    }
+                }
                 // Gradients may come from the plugin's reduced-precision tensor-core path at
                 // EVERY step: leapfrog with any deterministic gradient function is reversible
                 // and volume preserving (the endpoint gradient is also what the next
