@@ -174,6 +174,7 @@ class ChainSampler:
             # 37 chain-tiles of 256 (two full waves of the 148-CTA gradient GEMM) at D ~ 1000
             chunk_chains = max(256, int(round(9472 * 1000 / max(D, 1) / 256)) * 256)
         chunk_chains = max(1, min(int(chunk_chains), C_))
+        sizes = [min(chunk_chains, C_ - c) for c in range(0, C_, chunk_chains)]
         if getattr(self, "_hs", None) is None:
             self._hs = tuple(torch.cuda.Stream(self.device) for _ in range(3))
             self._h_draw = torch.empty(C_, D, dtype=self.dtype, device=self.device)
@@ -185,8 +186,8 @@ class ChainSampler:
             s.wait_stream(cur)
         # state loaded from the host (or never evaluated): the (logp, grad) cache is stale
         stale = theta_host is not None or not self._cache_valid.value
-        for c0 in range(0, C_, chunk_chains):
-            cn = min(chunk_chains, C_ - c0)
+        c0 = 0
+        for cn in sizes:
             valid = L.i32(0 if stale else 1)
             if theta_host is not None:
                 with torch.cuda.stream(s_in):
@@ -203,6 +204,7 @@ class ChainSampler:
             with torch.cuda.stream(s_out):
                 draw_h[c0:c0 + cn].copy_(self._h_draw[c0:c0 + cn], non_blocking=True)
                 logp_h[c0:c0 + cn].copy_(self._h_logp[c0:c0 + cn], non_blocking=True)
+            c0 += cn
         self._t += 1
         self.last_accept = self._h_acc
         self._cache_valid.value = 1              # every chunk refreshed its slice of the cache
