@@ -47,13 +47,13 @@ constexpr int UK = 16;       // UMMA K for bf16
 constexpr int CWID = 16;                               // chains per epilogue chunk
 constexpr int EDEPTH = 4;                              // ring depth per epilogue warp
 constexpr int ECHUNK_BYTES = 2 * CWID * 32 * 4;        // r + q of one chunk of one warp
-template <int MODE> struct Cfg {
+template <int MODE, bool PAIR = false> struct Cfg {
     // STEP stages are HALF k-blocks (32 k = 64-byte rows, SWIZZLE_64B): 4 x 24 KB keeps the same
     // 96 KB of operands in flight as 2 x 48 KB but with twice the pipeline granularity.
     static constexpr int KS = MODE == TC_MODE_STEP ? 32 : 64;          // k per stage
     static constexpr int STAGES = 4;
     static constexpr int A_BYTES = BM * KS * 2;
-    static constexpr int B_BYTES = BN * KS * 2;
+    static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * KS * 2;   // pair: each CTA stages half the chains
     static constexpr int SMEM_TILES = STAGES * (A_BYTES + B_BYTES);
     static constexpr int ERING = MODE == TC_MODE_STEP ? 8 * EDEPTH * ECHUNK_BYTES : 0;
     static constexpr int SMEM_BYTES = SMEM_TILES + ERING + 256 + 1024;  // + barriers + alignment slack
@@ -94,6 +94,47 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
         : "memory");
 }
+// ---- CTA pair (cta_group::2) helpers: the two CTAs of a cluster run ONE 256 x 256 MMA; each CTA
+// stages its 128 rows of A and HALF of B (128 of the 256 chains), the leader (rank 0) issues
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {   // same smem offset in CTA `rank`
+    uint32_t d;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(saddr), "r"(rank));
+    return d;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into OWN shared memory whose bytes are credited to the barrier `bar_cluster` (leader's)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on `bar`'s offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -112,6 +153,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 // kind::f16, A = B = bf16, D = f32, both K-major, M = 128, N = 256
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                            ((uint32_t)(BM >> 4) << 24);
+// CTA pair: M = 256 (two CTAs x 128 dims), N = 256
+constexpr uint32_t IDESC_PAIR = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                ((uint32_t)((2 * BM) >> 4) << 24);
 
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
     asm volatile(
@@ -197,7 +241,7 @@ struct StepArgs {
     __nv_bfloat16* q_lo_next;  // [C, Dp] or NULL
     float* g_out;         // [C, D] row-major, or tile-blocked when g_blocked
     int g_blocked;
-    int debug;            // BK_TC_DEBUG bits: 1 = skip TMA+MMA, 2 = skip epilogue global traffic
+    int debug;            // BK_TC_DEBUG bits: 1 = skip TMA+MMA, 2 = skip epilogue global traffic, 4 = load B on even stages only
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -207,21 +251,25 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int MODE>
+template <int MODE, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
            const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
            const StepArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    // 1024-byte alignment for the 128B swizzle atoms
+    // 1024-byte alignment for the 128B swizzle atoms (dynamic smem starts at the same offset in both
+    // CTAs of a pair, so the carve-up below is identical in both -- the pair MMA relies on that)
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    constexpr int STAGES = Cfg<MODE>::STAGES;
-    constexpr int SMEM_TILES = Cfg<MODE>::SMEM_TILES;
-    constexpr int KS = Cfg<MODE>::KS, A_BYTES = Cfg<MODE>::A_BYTES, B_BYTES = Cfg<MODE>::B_BYTES;
+    using C_ = Cfg<MODE, PAIR>;
+    constexpr int STAGES = C_::STAGES;
+    constexpr int SMEM_TILES = C_::SMEM_TILES;
+    constexpr int KS = C_::KS, A_BYTES = C_::A_BYTES, B_BYTES = C_::B_BYTES;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs)
+    const int n_cta = PAIR ? 2 : 1;
     constexpr int SPK = BK / KS;                               // stages per 64-wide k-block
     const uint32_t sA = base, sB = base + STAGES * A_BYTES;
     const uint32_t ering = base + SMEM_TILES;                 // STEP: per-warp r/q rings
-    const uint32_t bars = ering + Cfg<MODE>::ERING;
+    const uint32_t bars = ering + C_::ERING;
     auto full = [&](int s) { return bars + 8u * s; };
     auto empty = [&](int s) { return bars + 8u * (STAGES + s); };
     auto tfull = [&](int s) { return bars + 8u * (2 * STAGES + s); };
@@ -233,21 +281,35 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 32 * EPI_WARPS); }
+        // pair: the leader's tempty collects one arrival per epilogue WARP of both CTAs
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), PAIR ? 2 * EPI_WARPS : 32 * EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if constexpr (PAIR) cluster_sync_all();          // both CTAs' barriers exist before anything remote touches them
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                     "r"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                         "r"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                         "r"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const int64_t total_tiles = a.n_tiles * a.m_tiles;
+    // work units: single CTA -> tiles (n_tile, m_tile); pair -> (n_tile, pair of adjacent m_tiles), CTA `rank`
+    // of the cluster owning m_tile = 2 * m_pair + rank.  `unit` below enumerates them; first / stride per CTA.
+    const int m_units = PAIR ? a.m_tiles / 2 : a.m_tiles;
+    const int64_t total_tiles = a.n_tiles * m_units;
+    const int64_t unit0 = PAIR ? blockIdx.x / 2 : blockIdx.x, unit_stride = PAIR ? gridDim.x / 2 : gridDim.x;
+    auto m_tile_of = [&](int64_t unit) { return PAIR ? 2 * (int)(unit % m_units) + (int)rank : (int)(unit % m_units); };
     const int iters = a.n_pass * a.kblocks * SPK;
 
     if (warp == 0) {
@@ -255,9 +317,9 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         if (lane == 0 && !(a.debug & 1)) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_tile = (int)(tile % a.m_tiles);
-                const int64_t n_tile = tile / a.m_tiles;
+            for (int64_t tile = unit0; tile < total_tiles; tile += unit_stride) {
+                const int m_tile = m_tile_of(tile);
+                const int64_t n_tile = tile / m_units;
                 for (int it = 0; it < iters; ++it) {
                     const int pass = it / (a.kblocks * SPK), ks = it % (a.kblocks * SPK);
                     const int kb = ks / SPK, kx = (ks % SPK) * KS;   // 64-wide box, k offset inside it
@@ -265,20 +327,34 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                     const CUtensorMap* ma = pass == 2 ? &mapA1 : &mapA0;
                     const CUtensorMap* mb = pass == 1 ? &mapB1 : &mapB0;
                     mbar_wait(empty(stage), phase ^ 1u);
-                    mbar_expect_tx(full(stage), A_BYTES + B_BYTES);
-                    tma_load_2d(sA + stage * A_BYTES, ma, full(stage), kx, (m_tile * a.kblocks + kb) * BM);
-                    tma_load_2d(sB + stage * B_BYTES, mb, full(stage), kx,
-                                (int)((n_tile * a.kblocks + kb) * BN));
+                    if constexpr (PAIR) {
+                        // both CTAs load into their own shared memory; every byte is credited to the LEADER's
+                        // full barrier (the leader's MMA thread is the only consumer of the stage)
+                        const uint32_t fb = mapa_rank(full(stage), 0);
+                        if (rank == 0) mbar_expect_tx(full(stage), 2 * (A_BYTES + B_BYTES));
+                        tma_load_2d_pair(sA + stage * A_BYTES, ma, fb, kx, (m_tile * a.kblocks + kb) * BM);
+                        tma_load_2d_pair(sB + stage * B_BYTES, mb, fb, kx,
+                                         (int)((n_tile * a.kblocks + kb) * BN + rank * (BN / 2)));
+                    } else {
+                        const bool skip_b = (a.debug & 4) && (it & 1);   // timing experiment: half the B traffic
+                        mbar_expect_tx(full(stage), A_BYTES + (skip_b ? 0 : B_BYTES));
+                        tma_load_2d(sA + stage * A_BYTES, ma, full(stage), kx, (m_tile * a.kblocks + kb) * BM);
+                        if (!skip_b)
+                            tma_load_2d(sB + stage * B_BYTES, mb, full(stage), kx,
+                                        (int)((n_tile * a.kblocks + kb) * BN));
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one thread) =================
-        if (lane == 0 && (a.debug & 1)) {   // experiment: no GEMM, just hand the accumulators over
+        if (PAIR && rank != 0) {
+            // the peer CTA's MMA warp only took part in the TMEM allocation
+        } else if (lane == 0 && (a.debug & 1)) {   // experiment: no GEMM, just hand the accumulators over
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int64_t tile = unit0; tile < total_tiles; tile += unit_stride) {
                 mbar_wait(tempty(acc), acc_phase ^ 1u);
                 mbar_arrive(tfull(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -288,8 +364,8 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                mbar_wait(tempty(acc), acc_phase ^ 1u);   // epilogue drained this accumulator
+            for (int64_t tile = unit0; tile < total_tiles; tile += unit_stride) {
+                mbar_wait(tempty(acc), acc_phase ^ 1u);   // epilogue(s) drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
                 for (int it = 0; it < iters; ++it) {
@@ -297,13 +373,20 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                     tc_fence_after();
                     const uint32_t a0 = sA + stage * A_BYTES, b0 = sB + stage * B_BYTES;
 #pragma unroll
-                    for (int k = 0; k < KS / UK; ++k)
-                        umma(d_tmem, umma_desc<KS * 2>(a0 + k * UK * 2), umma_desc<KS * 2>(b0 + k * UK * 2),
-                             (it | k) != 0 ? 1u : 0u);
-                    umma_commit(empty(stage));            // smem slot reusable once these MMAs retire
+                    for (int k = 0; k < KS / UK; ++k) {
+                        if constexpr (PAIR)
+                            umma_pair(d_tmem, umma_desc<KS * 2>(a0 + k * UK * 2), umma_desc<KS * 2>(b0 + k * UK * 2),
+                                      IDESC_PAIR, (it | k) != 0 ? 1u : 0u);
+                        else
+                            umma(d_tmem, umma_desc<KS * 2>(a0 + k * UK * 2), umma_desc<KS * 2>(b0 + k * UK * 2),
+                                 (it | k) != 0 ? 1u : 0u);
+                    }
+                    // smem slot reusable once these MMAs retire (pair: in both CTAs)
+                    if constexpr (PAIR) umma_commit_pair(empty(stage)); else umma_commit(empty(stage));
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(tfull(acc));                  // accumulator ready for the epilogue
+                // accumulator ready for the epilogue (pair: each CTA's own 128 dims x 256 chains)
+                if constexpr (PAIR) umma_commit_pair(tfull(acc)); else umma_commit(tfull(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
@@ -316,9 +399,9 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         int acc = 0;
         uint32_t acc_phase = 0;
         if constexpr (MODE == TC_MODE_GRAD) {
-            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_tile = (int)(tile % a.m_tiles);
-                const int64_t n_tile = tile / a.m_tiles;
+            for (int64_t tile = unit0; tile < total_tiles; tile += unit_stride) {
+                const int m_tile = m_tile_of(tile);
+                const int64_t n_tile = tile / m_units;
                 const int d = m_tile * BM + quarter * 32 + lane;
                 const bool d_ok = d < a.D;
                 const float cv = (a.cvec && d_ok) ? a.cvec[d] : 0.0f;
@@ -341,7 +424,12 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(tempty(acc));
+                if constexpr (PAIR) {          // one arrival per warp on the LEADER's barrier
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty(acc), 0));
+                } else {
+                    mbar_arrive(tempty(acc));
+                }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         } else {
@@ -353,14 +441,14 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
             constexpr int NC = NCH * 32 / CWID;                 // chunks per warp per tile
             const bool no_mem = (a.debug & 2) != 0;
             const uint32_t ring = ering + (uint32_t)(warp - 2) * (EDEPTH * ECHUNK_BYTES);
-            const int64_t n_my = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+            const int64_t n_my = unit0 < total_tiles ? (total_tiles - unit0 + unit_stride - 1) / unit_stride : 0;
             const int64_t total_chunks = n_my * NC;
             const int row_in = lane >> 3, seg = lane & 7;       // cp.async: 4 rows x 8 x 16 B per instruction
             auto chunk_elem0 = [&](int64_t g) -> int64_t {      // element offset of (chain row 0, dim 0) of chunk g
-                const int64_t tile = blockIdx.x + (g / NC) * gridDim.x;
+                const int64_t tile = unit0 + (g / NC) * unit_stride;
                 const int ch = (int)(g % NC);
-                const int m_tile = (int)(tile % a.m_tiles);
-                const int64_t n_tile = tile / a.m_tiles;
+                const int m_tile = m_tile_of(tile);
+                const int64_t n_tile = tile / m_units;
                 return blk_index(n_tile * BN + half * NCH * 32 + ch * CWID, m_tile * BM + quarter * 32, a.m_tiles);
             };
             auto issue = [&](int64_t g) {
@@ -381,9 +469,9 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
 #pragma unroll
             for (int p = 0; p < EDEPTH - 1; ++p) issue(p);
             int64_t g = 0;
-            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_tile = (int)(tile % a.m_tiles);
-                const int64_t n_tile = tile / a.m_tiles;
+            for (int64_t tile = unit0; tile < total_tiles; tile += unit_stride) {
+                const int m_tile = m_tile_of(tile);
+                const int64_t n_tile = tile / m_units;
                 const int d = m_tile * BM + quarter * 32 + lane;
                 const bool d_ok = d < a.D;
                 const float cv = (a.cvec && d_ok) ? a.cvec[d] : 0.0f;
@@ -433,7 +521,12 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                         }
                 }
                 tc_fence_before();
-                mbar_arrive(tempty(acc));
+                if constexpr (PAIR) {          // one arrival per warp on the LEADER's barrier
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty(acc), 0));
+                } else {
+                    mbar_arrive(tempty(acc));
+                }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
             cp_async_wait<0>();
@@ -441,10 +534,15 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();      // both CTAs are done with the pair's TMEM and barriers
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
-                     : "memory");
+        if constexpr (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+                         : "memory");
     }
 }
 
@@ -671,11 +769,13 @@ static EncodeFn get_encode() {
 
 // bf16 row-major [rows, Dp] (pitch Dp), box = [box_rows x 64 k], 128B swizzle
 // box-blocked bf16 operand: a [n_boxes * box_rows, 64] matrix with 128-byte rows
-static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int Dp, int box_rows, int box_k) {
+// `blk_rows` = rows per stored box (the array's blocking); a load may fetch `box_rows` <= blk_rows of one
+static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int Dp, int box_rows, int box_k, int blk_rows = 0) {
     EncodeFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return BK_E_CUDA; }
-    const int64_t row_tiles = (rows + box_rows - 1) / box_rows;
-    cuuint64_t dims[2] = {(cuuint64_t)BK, (cuuint64_t)(row_tiles * (Dp / BK) * box_rows)};
+    if (!blk_rows) blk_rows = box_rows;
+    const int64_t row_tiles = (rows + blk_rows - 1) / blk_rows;
+    cuuint64_t dims[2] = {(cuuint64_t)BK, (cuuint64_t)(row_tiles * (Dp / BK) * blk_rows)};
     cuuint64_t strides[1] = {(cuuint64_t)BK * 2};
     cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
     cuuint32_t el[2] = {1, 1};
@@ -691,12 +791,21 @@ static int launch_tc(const Model& m, const StepArgs& a, const __nv_bfloat16* b_h
                      cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        BK_CUDA(cudaFuncSetAttribute(k_dense_tc<TC_MODE_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg<TC_MODE_STEP>::SMEM_BYTES));
-        BK_CUDA(cudaFuncSetAttribute(k_dense_tc<TC_MODE_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg<TC_MODE_GRAD>::SMEM_BYTES));
+        BK_CUDA(cudaFuncSetAttribute(k_dense_tc<TC_MODE_STEP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg<TC_MODE_STEP, false>::SMEM_BYTES));
+        BK_CUDA(cudaFuncSetAttribute(k_dense_tc<TC_MODE_GRAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg<TC_MODE_GRAD, false>::SMEM_BYTES));
+        BK_CUDA(cudaFuncSetAttribute(k_dense_tc<TC_MODE_STEP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg<TC_MODE_STEP, true>::SMEM_BYTES));
+        BK_CUDA(cudaFuncSetAttribute(k_dense_tc<TC_MODE_GRAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg<TC_MODE_GRAD, true>::SMEM_BYTES));
         attr = true;
     }
+    // CTA pairs (cta_group::2): two adjacent dim-tiles share one 256 x 256 MMA and each CTA stages only
+    // half of the chain tile -- needs an even number of dim-tiles; BK_TC_PAIR=0 selects the single-CTA kernel
+    static int pair_env = -1;
+    if (pair_env < 0) { const char* e = getenv("BK_TC_PAIR"); pair_env = (e && e[0] == '0') ? 0 : 1; }
+    const bool pair = pair_env && a.m_tiles % 2 == 0 && !(a.debug & 5);
     static int sms = 0;
     if (!sms) {
         int dev = 0;
@@ -708,16 +817,45 @@ static int launch_tc(const Model& m, const StepArgs& a, const __nv_bfloat16* b_h
     const int bk = a.mode == TC_MODE_STEP ? Cfg<TC_MODE_STEP>::KS : Cfg<TC_MODE_GRAD>::KS;
     if ((rc = make_map(&mA0, m.P_hi, m.Dp, (int)m.Dp, BM, bk))) return rc;
     if ((rc = make_map(&mA1, m.P_lo, m.Dp, (int)m.Dp, BM, bk))) return rc;
-    if ((rc = make_map(&mB0, b_hi, a.C, (int)m.Dp, BN, bk))) return rc;
-    if ((rc = make_map(&mB1, b_lo ? b_lo : b_hi, a.C, (int)m.Dp, BN, bk))) return rc;
+    const int brows = pair ? BN / 2 : BN;      // pair: each CTA loads half of a stored 256-row box
+    if ((rc = make_map(&mB0, b_hi, a.C, (int)m.Dp, brows, bk, BN))) return rc;
+    if ((rc = make_map(&mB1, b_lo ? b_lo : b_hi, a.C, (int)m.Dp, brows, bk, BN))) return rc;
+    const int tag = a.mode == TC_MODE_STEP ? BK_PROF_STEP : BK_PROF_GRAD;
+    if (pair) {
+        const int64_t units = a.n_tiles * (a.m_tiles / 2);
+        const int64_t max_pairs = sms / 2;
+        const unsigned grid = 2u * (unsigned)(units < max_pairs ? units : max_pairs);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(THREADS);
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        prof_begin(tag, st);
+        cudaError_t e;
+        if (a.mode == TC_MODE_STEP) {
+            cfg.dynamicSmemBytes = Cfg<TC_MODE_STEP, true>::SMEM_BYTES;
+            e = cudaLaunchKernelEx(&cfg, k_dense_tc<TC_MODE_STEP, true>, mA0, mA1, mB0, mB1, a);
+        } else {
+            cfg.dynamicSmemBytes = Cfg<TC_MODE_GRAD, true>::SMEM_BYTES;
+            e = cudaLaunchKernelEx(&cfg, k_dense_tc<TC_MODE_GRAD, true>, mA0, mA1, mB0, mB1, a);
+        }
+        prof_end(tag, st);
+        if (e != cudaSuccess) { set_error("pair launch failed: %s", cudaGetErrorString(e)); return BK_E_CUDA; }
+        count_launch();
+        return BK_OK;
+    }
     const int64_t tiles = a.n_tiles * a.m_tiles;
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-    const int tag = a.mode == TC_MODE_STEP ? BK_PROF_STEP : BK_PROF_GRAD;
     prof_begin(tag, st);
     if (a.mode == TC_MODE_STEP)
-        k_dense_tc<TC_MODE_STEP><<<grid, THREADS, Cfg<TC_MODE_STEP>::SMEM_BYTES, st>>>(mA0, mA1, mB0, mB1, a);
+        k_dense_tc<TC_MODE_STEP, false><<<grid, THREADS, Cfg<TC_MODE_STEP, false>::SMEM_BYTES, st>>>(mA0, mA1, mB0, mB1, a);
     else
-        k_dense_tc<TC_MODE_GRAD><<<grid, THREADS, Cfg<TC_MODE_GRAD>::SMEM_BYTES, st>>>(mA0, mA1, mB0, mB1, a);
+        k_dense_tc<TC_MODE_GRAD, false><<<grid, THREADS, Cfg<TC_MODE_GRAD, false>::SMEM_BYTES, st>>>(mA0, mA1, mB0, mB1, a);
     prof_end(tag, st);
     BK_LAUNCH_CHECK();
     return BK_OK;
