@@ -45,13 +45,16 @@ constexpr int UK = 16;       // UMMA K for bf16
 // 2 operand stages, and the freed 128 KB is a per-warp cp.async ring that keeps
 // EDEPTH-1 chunks (16 chains x 32 dims of r and q = 4 KB) per epilogue warp in flight.
 constexpr int CWID = 16;                               // chains per epilogue chunk
-constexpr int EDEPTH = 4;                              // ring depth per epilogue warp
+constexpr int EDEPTH_MAX = 4;                          // ring depth per epilogue warp (Cfg::EDEPTH)
 constexpr int ECHUNK_BYTES = 2 * CWID * 32 * 4;        // r + q of one chunk of one warp
 template <int MODE, bool PAIR = false> struct Cfg {
     // STEP stages are HALF k-blocks (32 k = 64-byte rows, SWIZZLE_64B): 4 x 24 KB keeps the same
     // 96 KB of operands in flight as 2 x 48 KB but with twice the pipeline granularity.
     static constexpr int KS = MODE == TC_MODE_STEP ? 32 : 64;          // k per stage
-    static constexpr int STAGES = 4;
+    // pair + STEP: the GEMM side is bound by operand bytes in flight (TMA latency), so it trades one ring
+    // slot per epilogue warp (32 KB) for four more 16 KB operand stages
+    static constexpr int STAGES = (PAIR && MODE == TC_MODE_STEP) ? 8 : 4;
+    static constexpr int EDEPTH = (PAIR && MODE == TC_MODE_STEP) ? 3 : EDEPTH_MAX;
     static constexpr int A_BYTES = BM * KS * 2;
     static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * KS * 2;   // pair: each CTA stages half the chains
     static constexpr int SMEM_TILES = STAGES * (A_BYTES + B_BYTES);
@@ -440,6 +443,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
             // registers:  q_next = q + ((q - q_prev) + eps^2*m*g) ; q_hi(next operand) = bf16(q_next).
             constexpr int NC = NCH * 32 / CWID;                 // chunks per warp per tile
             const bool no_mem = (a.debug & 2) != 0;
+            constexpr int EDEPTH = C_::EDEPTH;
             const uint32_t ring = ering + (uint32_t)(warp - 2) * (EDEPTH * ECHUNK_BYTES);
             const int64_t n_my = unit0 < total_tiles ? (total_tiles - unit0 + unit_stride - 1) / unit_stride : 0;
             const int64_t total_chunks = n_my * NC;
