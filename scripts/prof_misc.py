@@ -1,4 +1,4 @@
-"""Small profiling drivers: python scripts/prof_misc.py {c1|smc|c3|ess|acf}"""
+"""Small profiling drivers: python scripts/prof_misc.py {c1|smc|c3|ess|acf|sort}"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -20,6 +20,9 @@ elif w == "c3":
     X, y = HierLogReg.c3_data(N, Dx, seed=0)
     s = bk.HMCDiag(bk.HierLogReg(X, y), 0.01, 10, init=np.random.default_rng(1).normal(size=(C, Dx + 2)) * 0.1, seed=0)
     s.sample_n(3)
+elif w == "sort":
+    x = torch.randn(10000, 2048, 1, device="cuda")
+    bk.rank_normalized_rhat(x, draws_first=True); bk.rank_normalized_rhat(x, draws_first=True)
 elif w in ("ess", "acf"):
     N, S = 10000, 25600 if w == "ess" else 4096
     g = torch.Generator(device="cuda"); g.manual_seed(0)
