@@ -108,7 +108,10 @@ __global__ void k_radix_scan_digits(const uint32_t* __restrict__ digit_tot, uint
     }
 }
 
-// stable scatter: element order inside a tile is (warp, item, lane)
+// stable scatter: element order inside a tile is (warp, item, lane).  The tile is first sorted by digit
+// INSIDE shared memory (each element's tile-local position = exclusive digit offset + its stable rank
+// among equal digits), then written out in that order: elements with equal digits are neighbours, so
+// each digit's run lands as one contiguous burst instead of 2048 isolated 4-byte writes.
 template <typename K>
 __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const K* __restrict__ keys_in,
                                                               const uint32_t* __restrict__ vals_in, int64_t n,
@@ -116,7 +119,12 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const K* __restric
                                                               int64_t nb, const uint32_t* __restrict__ digit_base,
                                                               K* __restrict__ keys_out,
                                                               uint32_t* __restrict__ vals_out) {
-    __shared__ uint32_t cnt[RS_WARPS][RS_BINS + 1];     // per-warp digit counts, then running offsets
+    __shared__ uint32_t cnt[RS_WARPS][RS_BINS + 1];     // per-warp digit counts, then running tile-local offsets
+    __shared__ uint32_t lbase[RS_BINS + 1];             // tile-local exclusive digit offsets
+    __shared__ uint32_t gbase[RS_BINS];                 // global position of the tile's first element per digit
+    __shared__ uint32_t wtot[RS_THREADS / 32];
+    __shared__ K skey[RS_TILE];
+    __shared__ uint32_t sval[RS_TILE];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RS_WARPS * (RS_BINS + 1); i += RS_THREADS) (&cnt[0][0])[i] = 0;
     __syncthreads();
@@ -129,32 +137,69 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const K* __restric
         const bool ok = i < n;
         key[j] = ok ? keys_in[i] : (K)0;
         val[j] = ok ? vals_in[i] : 0u;
-        dig[j] = ok ? ((uint32_t)(key[j] >> shift) & 0xffu) : (uint32_t)RS_BINS;   // bin 256: padding, never written
+        dig[j] = ok ? ((uint32_t)(key[j] >> shift) & 0xffu) : (uint32_t)RS_BINS;   // bin 256: padding, sorts last
         atomicAdd(&cnt[w][dig[j]], 1u);
     }
     __syncthreads();
-    // per digit: exclusive scan over the warps, plus this tile's global offset
-    for (int d = threadIdx.x; d < RS_BINS; d += RS_THREADS) {
-        uint32_t run = digit_base[d] + hist[(int64_t)d * nb + blockIdx.x];
+    // thread d: digit d's total over the warps -> exclusive scan over the 256 digits (block scan)
+    static_assert(RS_THREADS == RS_BINS, "one thread per digit");
+    uint32_t tot = 0;
+#pragma unroll
+    for (int k = 0; k < RS_WARPS; ++k) tot += cnt[k][threadIdx.x];
+    uint32_t inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wtot[w] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int k = 0; k < w; ++k) woff += wtot[k];
+    const uint32_t excl = woff + inc - tot;
+    {
+        const int d = threadIdx.x;
+        lbase[d] = excl;
+        if (d == RS_BINS - 1) lbase[RS_BINS] = excl + tot;          // padding elements go behind every digit
+        gbase[d] = digit_base[d] + hist[(int64_t)d * nb + blockIdx.x];
+        uint32_t run = excl;                                        // per-warp tile-local starting offsets
 #pragma unroll
         for (int k = 0; k < RS_WARPS; ++k) {
             const uint32_t c = cnt[k][d];
             cnt[k][d] = run;
             run += c;
         }
+        if (d == 0) {
+            uint32_t pr = 0;
+            for (int k = 0; k < RS_WARPS; ++k) { const uint32_t c = cnt[k][RS_BINS]; cnt[k][RS_BINS] = pr; pr += c; }
+        }
     }
     __syncthreads();
+    const uint32_t pad0 = lbase[RS_BINS];
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; ++j) {
         const uint32_t peers = __match_any_sync(0xffffffffu, dig[j]);
         const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-        const uint32_t pos = cnt[w][dig[j]] + rank;
+        uint32_t pos = cnt[w][dig[j]] + rank;
         __syncwarp();
         if (rank == 0) cnt[w][dig[j]] += __popc(peers);
         __syncwarp();
-        if (dig[j] < RS_BINS) {
-            keys_out[pos] = key[j];
-            vals_out[pos] = val[j];
+        if (dig[j] == RS_BINS) pos += pad0;
+        skey[pos] = key[j];
+        sval[pos] = val[j];
+    }
+    __syncthreads();
+    // write out in tile-sorted order: thread i handles local positions i, i + 256, ...
+    const int64_t valid = n - (int64_t)blockIdx.x * RS_TILE < RS_TILE ? n - (int64_t)blockIdx.x * RS_TILE : RS_TILE;
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        const int i = j * RS_THREADS + threadIdx.x;
+        if (i < valid) {
+            const K k = skey[i];
+            const uint32_t d = (uint32_t)(k >> shift) & 0xffu;
+            const uint32_t pos = gbase[d] + ((uint32_t)i - lbase[d]);
+            keys_out[pos] = k;
+            vals_out[pos] = sval[i];
         }
     }
 }
