@@ -445,34 +445,42 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
             const bool no_mem = (a.debug & 2) != 0;
             constexpr int EDEPTH = C_::EDEPTH;
             const uint32_t ring = ering + (uint32_t)(warp - 2) * (EDEPTH * ECHUNK_BYTES);
-            const int64_t n_my = unit0 < total_tiles ? (total_tiles - unit0 + unit_stride - 1) / unit_stride : 0;
-            const int64_t total_chunks = n_my * NC;
             const int row_in = lane >> 3, seg = lane & 7;       // cp.async: 4 rows x 8 x 16 B per instruction
-            auto chunk_elem0 = [&](int64_t g) -> int64_t {      // element offset of (chain row 0, dim 0) of chunk g
-                const int64_t tile = unit0 + (g / NC) * unit_stride;
-                const int ch = (int)(g % NC);
-                const int m_tile = m_tile_of(tile);
-                const int64_t n_tile = tile / m_units;
-                return blk_index(n_tile * BN + half * NCH * 32 + ch * CWID, m_tile * BM + quarter * 32, a.m_tiles);
-            };
-            auto issue = [&](int64_t g) {
-                if (g < total_chunks && !no_mem) {
-                    const int64_t e0 = chunk_elem0(g);
-                    const uint32_t dst = ring + (uint32_t)(g % EDEPTH) * ECHUNK_BYTES;
+            // A unit's 256 x 128 patch of the tile-blocked arrays starts at (n_tile * m_tiles + m_tile) * BN * BM
+            // = (pair ? 2 * unit + rank : unit) * BN * BM: no divisions on the streaming side.  Inside the patch
+            // this warp's chunks are CWID * BM elements apart.
+            const int64_t warp_off = (int64_t)(half * NCH * 32) * BM + quarter * 32;
+            auto patch0 = [&](int64_t unit) -> int64_t { return (PAIR ? 2 * unit + rank : unit) * (int64_t)(BN * BM) + warp_off; };
+            // prefetch cursor: next chunk to request (tile, chunk in tile, ring slot, source pointers of this lane)
+            int64_t pf_tile = unit0;
+            int pf_ch = 0;
+            uint32_t pf_dst = ring + (uint32_t)(row_in * 128 + seg * 16);
+            int pf_slot = 0;
+            int64_t pf_e = patch0(pf_tile) + (int64_t)row_in * BM + seg * 4;
+            auto issue = [&]() {
+                if (pf_tile < total_tiles && !no_mem) {
+                    const float* sp = a.q_prev + pf_e;
+                    const float* sc = a.q_cur + pf_e;
 #pragma unroll
                     for (int it = 0; it < CWID / 4; ++it) {
-                        const int row = it * 4 + row_in;
-                        const int64_t eo = e0 + (int64_t)row * BM + seg * 4;
-                        const uint32_t so = (uint32_t)(row * 128 + seg * 16);
-                        cp_async16(dst + so, a.q_prev + eo);
-                        cp_async16(dst + CWID * 128 + so, a.q_cur + eo);
+                        cp_async16(pf_dst + it * 512, sp + it * 4 * BM);
+                        cp_async16(pf_dst + CWID * 128 + it * 512, sc + it * 4 * BM);
+                    }
+                    pf_e += CWID * BM;
+                    if (++pf_ch == NC) {
+                        pf_ch = 0;
+                        pf_tile += unit_stride;
+                        pf_e = patch0(pf_tile) + (int64_t)row_in * BM + seg * 4;
                     }
                 }
                 cp_async_commit();
+                pf_dst += ECHUNK_BYTES;
+                if (++pf_slot == EDEPTH) { pf_slot = 0; pf_dst -= EDEPTH * ECHUNK_BYTES; }
             };
 #pragma unroll
-            for (int p = 0; p < EDEPTH - 1; ++p) issue(p);
-            int64_t g = 0;
+            for (int p = 0; p < EDEPTH - 1; ++p) issue();
+            uint32_t src = ring + (uint32_t)lane * 4;           // consume cursor (this lane's dim column of the chunk)
+            int slot = 0;
             for (int64_t tile = unit0; tile < total_tiles; tile += unit_stride) {
                 const int m_tile = m_tile_of(tile);
                 const int64_t n_tile = tile / m_units;
@@ -483,41 +491,74 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                 const uint32_t t0 = tmem_base + (uint32_t)acc * BN + ((uint32_t)(quarter * 32) << 16) +
                                     (uint32_t)(half * NCH * 32);
                 const int64_t cbase = n_tile * BN + half * NCH * 32;
-                const bool full_tile = d_ok && cbase + NCH * 32 <= a.C;
-                const int64_t e0 = blk_index(cbase, d, a.m_tiles);
-                float* qw = a.q_prev + e0;      // q_{n+1} replaces q_{n-1}
+                // warp-uniform: every lane's dim is real and all of this warp's chains exist -> no predicates
+                const bool fast = __all_sync(0xffffffffu, d_ok && cbase + NCH * 32 <= a.C) && !no_mem;
+                float* qw = a.q_prev + patch0(tile) + lane;      // q_{n+1} replaces q_{n-1}
                 const int64_t b0i = box_index(cbase, d, a.kblocks, BN);
                 __nv_bfloat16* hw = a.q_hi_next + b0i;
                 __nv_bfloat16* lw = a.q_lo_next ? a.q_lo_next + b0i : nullptr;
                 mbar_wait(tfull(acc), acc_phase);
                 tc_fence_after();
 #pragma unroll 1
-                for (int ch = 0; ch < NC; ++ch, ++g) {
-                    issue(g + EDEPTH - 1);
-                    cp_async_wait<EDEPTH - 1>();      // chunk g has landed
+                for (int ch = 0; ch < NC; ++ch) {
+                    issue();
+                    cp_async_wait<EDEPTH - 1>();      // this chunk has landed
                     __syncwarp();
                     uint32_t v[CWID];
                     tmem_ld16(t0 + ch * CWID, v);
-                    const uint32_t src = ring + (uint32_t)(g % EDEPTH) * ECHUNK_BYTES + (uint32_t)lane * 4;
-                    const int64_t o = (int64_t)ch * CWID * BM, ob = (int64_t)ch * CWID * BK;
+                    if (fast) {
+                        if (lw == nullptr) {
 #pragma unroll
-                    for (int j = 0; j < CWID; ++j) {
-                        float pj, qj;
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pj) : "r"(src + j * 128));
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qj) : "r"(src + CWID * 128 + j * 128));
-                        if (!no_mem && (full_tile || (d_ok && cbase + ch * CWID + j < a.C))) {
-                            const float gj = cv - __uint_as_float(v[j]);
-                            // eps*r_{n+1/2} = eps*r_{n-1/2} + eps^2*m*g ;  q_{n+1} = q_n + eps*r_{n+1/2}
-                            const float qn = qj + fmaf(em2, gj, qj - pj);
-                            __stcs(qw + o + (int64_t)j * BM, qn);
-                            const __nv_bfloat16 hi = __float2bfloat16_rn(qn);
-                            hw[ob + (int64_t)j * BK] = hi;
-                            if (lw) lw[ob + (int64_t)j * BK] = __float2bfloat16_rn(qn - __bfloat162float(hi));
+                            for (int j = 0; j < CWID; ++j) {
+                                float pj, qj;
+                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pj) : "r"(src + j * 128));
+                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qj) : "r"(src + CWID * 128 + j * 128));
+                                const float gj = cv - __uint_as_float(v[j]);
+                                // eps*r_{n+1/2} = eps*r_{n-1/2} + eps^2*m*g ;  q_{n+1} = q_n + eps*r_{n+1/2}
+                                const float qn = qj + fmaf(em2, gj, qj - pj);
+                                __stcs(qw + j * BM, qn);
+                                hw[j * BK] = __float2bfloat16_rn(qn);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CWID; ++j) {
+                                float pj, qj;
+                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pj) : "r"(src + j * 128));
+                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qj) : "r"(src + CWID * 128 + j * 128));
+                                const float gj = cv - __uint_as_float(v[j]);
+                                const float qn = qj + fmaf(em2, gj, qj - pj);
+                                __stcs(qw + j * BM, qn);
+                                const __nv_bfloat16 hi = __float2bfloat16_rn(qn);
+                                hw[j * BK] = hi;
+                                lw[j * BK] = __float2bfloat16_rn(qn - __bfloat162float(hi));
+                            }
+                        }
+                    } else if (!no_mem) {
+#pragma unroll
+                        for (int j = 0; j < CWID; ++j) {
+                            float pj, qj;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pj) : "r"(src + j * 128));
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qj) : "r"(src + CWID * 128 + j * 128));
+                            if (d_ok && cbase + ch * CWID + j < a.C) {
+                                const float gj = cv - __uint_as_float(v[j]);
+                                const float qn = qj + fmaf(em2, gj, qj - pj);
+                                __stcs(qw + j * BM, qn);
+                                const __nv_bfloat16 hi = __float2bfloat16_rn(qn);
+                                hw[j * BK] = hi;
+                                if (lw) lw[j * BK] = __float2bfloat16_rn(qn - __bfloat162float(hi));
+                            }
                         }
                     }
+                    qw += CWID * BM;
+                    hw += CWID * BK;
+                    if (lw) lw += CWID * BK;
+                    src += ECHUNK_BYTES;
+                    if (++slot == EDEPTH) { slot = 0; src -= EDEPTH * ECHUNK_BYTES; }
                     __syncwarp();                     // stage may be refilled by the next issue
                 }
                 if (!d_ok && !no_mem) {   // pad dim (last dim-tile only): keep the next operand's padding zero
+                    hw -= NC * CWID * BK;
+                    if (lw) lw -= NC * CWID * BK;
                     for (int j = 0; j < NCH * 32; ++j)
                         if (cbase + j < a.C) {
                             hw[(int64_t)j * BK] = __float2bfloat16_rn(0.f);
