@@ -53,8 +53,12 @@ template <int MODE, bool PAIR = false> struct Cfg {
     static constexpr int KS = MODE == TC_MODE_STEP ? 32 : 64;          // k per stage
     // pair + STEP: the GEMM side is bound by operand bytes in flight (TMA latency), so it trades one ring
     // slot per epilogue warp (32 KB) for four more 16 KB operand stages
-    static constexpr int STAGES = (PAIR && MODE == TC_MODE_STEP) ? 8 : 4;
-    static constexpr int EDEPTH = (PAIR && MODE == TC_MODE_STEP) ? 3 : EDEPTH_MAX;
+#ifndef BK_STEP_STAGES
+#define BK_STEP_STAGES 8
+#define BK_STEP_EDEPTH 3
+#endif
+    static constexpr int STAGES = (PAIR && MODE == TC_MODE_STEP) ? BK_STEP_STAGES : 4;
+    static constexpr int EDEPTH = (PAIR && MODE == TC_MODE_STEP) ? BK_STEP_EDEPTH : EDEPTH_MAX;
     static constexpr int A_BYTES = BM * KS * 2;
     static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * KS * 2;   // pair: each CTA stages half the chains
     static constexpr int SMEM_TILES = STAGES * (A_BYTES + B_BYTES);
@@ -62,7 +66,11 @@ template <int MODE, bool PAIR = false> struct Cfg {
     static constexpr int SMEM_BYTES = SMEM_TILES + ERING + 256 + 1024;  // + barriers + alignment slack
 };
 constexpr int EPI_WARPS = 8;            // 2 per TMEM lane quarter (column halves); ring sized for 8
-constexpr int THREADS = 64 + 32 * EPI_WARPS;
+// + one signalling warp (fused STEP launches: publishes finished tiles to the other clusters, so the
+// gpu-scope release -- which waits for the SM's outstanding stores -- never stalls a streaming warp)
+constexpr int SIG_WARP = 2 + EPI_WARPS;
+constexpr int THREADS = 64 + 32 * EPI_WARPS + 32;
+constexpr int SIG_SLOTS = 4;
 constexpr uint32_t TMEM_COLS = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -114,7 +122,10 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default semantics (.release.cta): the cluster-scope release form costs a MEMBAR.ALL + ERRBAR that waits for
+    // every outstanding global store of the warp; the consumer (MMA issuer) only needs the TMEM reads to be
+    // complete, which tcgen05.wait::ld + tcgen05.fence::before_thread_sync guarantee
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into OWN shared memory whose bytes are credited to the barrier `bar_cluster` (leader's)
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int x, int y) {
@@ -226,6 +237,15 @@ __device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&v)[16
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait + register dependency: nothing that reads v may be scheduled above the wait
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]),
+                   "+r"(v[15])
+                 :
+                 : "memory");
+}
 
 struct StepArgs {
     int mode;          // TC_MODE_STEP | TC_MODE_GRAD
@@ -239,12 +259,20 @@ struct StepArgs {
     const float* metric;  // [D] or NULL
     const float* cvec;    // [D] P*mu or NULL
     float* q_prev;        // tile-blocked (STEP: q_{n-1} in, q_{n+1} out)
-    const float* q_cur;   // tile-blocked (STEP: q_n, read only)
-    __nv_bfloat16* q_hi_next;  // [C, Dp] (STEP)
-    __nv_bfloat16* q_lo_next;  // [C, Dp] or NULL
+    float* q_cur;         // tile-blocked (STEP: q_n, read only within a step; the two swap roles every fused step)
+    __nv_bfloat16* q_hi_next;  // [C, Dp] (STEP): operand written by even fused steps (0, 2, ...)
+    __nv_bfloat16* q_hi_cur;   // operand READ by step 0 (mapB0) = written by odd fused steps; multi-step launches only
+    __nv_bfloat16* q_lo_next;  // [C, Dp] or NULL: low half of the LAST fused step's operand
+    // Fused leapfrog steps (STEP + pair only): one persistent launch runs n_steps steps.  Step s of chain-tile j
+    // needs the bf16 operand rows all m_tiles dim-tiles of (s-1, j) wrote: every epilogue warp adds 1 to
+    // sync[(s-1) * n_tiles + j] (release, gpu scope) when its part of the tile is written; the TMA producers
+    // spin (acquire) until it reaches m_tiles * EPI_WARPS.  Zeroed by the host before the launch.
+    int n_steps;
+    uint32_t* sync;
     float* g_out;         // [C, D] row-major, or tile-blocked when g_blocked
     int g_blocked;
-    int debug;            // BK_TC_DEBUG bits: 1 = skip TMA+MMA, 2 = skip epilogue global traffic, 4 = load B on even stages only
+    int debug;            // BK_TC_DEBUG bits: 1 = skip TMA+MMA, 2 = skip epilogue global traffic, 4 = load B on even stages only,
+                          // 8 (with 1) = no accumulator handshake (free-running epilogue), 16 = accumulator never read
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -253,6 +281,16 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 template <int MODE, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -278,6 +316,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     auto tfull = [&](int s) { return bars + 8u * (2 * STAGES + s); };
     auto tempty = [&](int s) { return bars + 8u * (2 * STAGES + 2 + s); };
     const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+    auto twritten = [&](uint32_t k) { return bars + 8u * (2 * STAGES + 5 + (k % SIG_SLOTS)); };
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -286,6 +325,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
         // pair: the leader's tempty collects one arrival per epilogue WARP of both CTAs
         for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), PAIR ? 2 * EPI_WARPS : 32 * EPI_WARPS); }
+        for (int s = 0; s < SIG_SLOTS; ++s) mbar_init(twritten(s), EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if constexpr (PAIR) cluster_sync_all();          // both CTAs' barriers exist before anything remote touches them
@@ -314,21 +354,30 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     const int64_t unit0 = PAIR ? blockIdx.x / 2 : blockIdx.x, unit_stride = PAIR ? gridDim.x / 2 : gridDim.x;
     auto m_tile_of = [&](int64_t unit) { return PAIR ? 2 * (int)(unit % m_units) + (int)rank : (int)(unit % m_units); };
     const int iters = a.n_pass * a.kblocks * SPK;
+    const int n_steps = (MODE == TC_MODE_STEP && PAIR && a.n_steps > 1) ? a.n_steps : 1;
 
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0 && !(a.debug & 1)) {
             int stage = 0;
             uint32_t phase = 0;
+            const uint32_t sync_full = (uint32_t)a.m_tiles;      // one count per CTA that writes the chain-tile
+            for (int step = 0; step < n_steps; ++step)
             for (int64_t tile = unit0; tile < total_tiles; tile += unit_stride) {
                 const int m_tile = m_tile_of(tile);
                 const int64_t n_tile = tile / m_units;
+                if (step > 0) {      // every dim-tile of this chain-tile has written the previous step's operand
+                    const uint32_t* flag = a.sync + (int64_t)(step - 1) * a.n_tiles + n_tile;
+                    while (ld_acquire_gpu(flag) < sync_full) __nanosleep(64);
+                    fence_proxy_async_all();     // generic-proxy writes (other CTAs) -> this thread's TMA reads
+                }
                 for (int it = 0; it < iters; ++it) {
                     const int pass = it / (a.kblocks * SPK), ks = it % (a.kblocks * SPK);
                     const int kb = ks / SPK, kx = (ks % SPK) * KS;   // 64-wide box, k offset inside it
-                    // pass 0: (A_hi, B_hi)  pass 1: (A_hi, B_lo)  pass 2: (A_lo, B_hi)
+                    // pass 0: (A_hi, B_hi)  pass 1: (A_hi, B_lo)  pass 2: (A_lo, B_hi);
+                    // fused steps (n_pass = 1): the operand buffers alternate, mapB0 on even steps, mapB1 on odd
                     const CUtensorMap* ma = pass == 2 ? &mapA1 : &mapA0;
-                    const CUtensorMap* mb = pass == 1 ? &mapB1 : &mapB0;
+                    const CUtensorMap* mb = (pass == 1 || (step & 1)) ? &mapB1 : &mapB0;
                     mbar_wait(empty(stage), phase ^ 1u);
                     if constexpr (PAIR) {
                         // both CTAs load into their own shared memory; every byte is credited to the LEADER's
@@ -354,12 +403,15 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         // ================= MMA issuer (one thread) =================
         if (PAIR && rank != 0) {
             // the peer CTA's MMA warp only took part in the TMEM allocation
+        } else if (lane == 0 && (a.debug & 8)) {   // experiment: nothing to hand over
         } else if (lane == 0 && (a.debug & 1)) {   // experiment: no GEMM, just hand the accumulators over
             int acc = 0;
             uint32_t acc_phase = 0;
+            for (int step = 0; step < n_steps; ++step)
             for (int64_t tile = unit0; tile < total_tiles; tile += unit_stride) {
                 mbar_wait(tempty(acc), acc_phase ^ 1u);
                 mbar_arrive(tfull(acc));
+                if constexpr (PAIR) mbar_arrive_cluster(mapa_rank(tfull(acc), 1));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         } else if (lane == 0) {
@@ -367,6 +419,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            for (int step = 0; step < n_steps; ++step)
             for (int64_t tile = unit0; tile < total_tiles; tile += unit_stride) {
                 mbar_wait(tempty(acc), acc_phase ^ 1u);   // epilogue(s) drained this accumulator
                 tc_fence_after();
@@ -391,6 +444,20 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                 // accumulator ready for the epilogue (pair: each CTA's own 128 dims x 256 chains)
                 if constexpr (PAIR) umma_commit_pair(tfull(acc)); else umma_commit(tfull(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else if (warp == SIG_WARP) {
+        // ================= signaller (fused STEP launches) =================
+        // Epilogue warps arrive on a CTA-local barrier when their part of a tile is written; this thread then
+        // releases the tile at gpu scope (cumulative over the writes it observed through the barrier).
+        if constexpr (MODE == TC_MODE_STEP && PAIR) {
+            if (lane == 0 && n_steps > 1) {
+                uint32_t k = 0;
+                for (int step = 0; step < n_steps - 1; ++step)
+                    for (int64_t tile = unit0; tile < total_tiles; tile += unit_stride, ++k) {
+                        mbar_wait(twritten(k), (k / SIG_SLOTS) & 1u);
+                        red_release_gpu_add(a.sync + (int64_t)step * a.n_tiles + tile / m_units, 1u);
+                    }
             }
         }
     } else {
@@ -453,14 +520,17 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
             auto patch0 = [&](int64_t unit) -> int64_t { return (PAIR ? 2 * unit + rank : unit) * (int64_t)(BN * BM) + warp_off; };
             // prefetch cursor: next chunk to request (tile, chunk in tile, ring slot, source pointers of this lane)
             int64_t pf_tile = unit0;
-            int pf_ch = 0;
+            int pf_ch = 0, pf_step = 0;
+            const float* pf_prev = a.q_prev;     // roles swap every fused step
+            const float* pf_cur = a.q_cur;
             uint32_t pf_dst = ring + (uint32_t)(row_in * 128 + seg * 16);
             int pf_slot = 0;
             int64_t pf_e = patch0(pf_tile) + (int64_t)row_in * BM + seg * 4;
+            if (unit0 >= total_tiles) pf_step = n_steps;      // no work for this CTA
             auto issue = [&]() {
-                if (pf_tile < total_tiles && !no_mem) {
-                    const float* sp = a.q_prev + pf_e;
-                    const float* sc = a.q_cur + pf_e;
+                if (pf_step < n_steps && !no_mem) {
+                    const float* sp = pf_prev + pf_e;
+                    const float* sc = pf_cur + pf_e;
 #pragma unroll
                     for (int it = 0; it < CWID / 4; ++it) {
                         cp_async16(pf_dst + it * 512, sp + it * 4 * BM);
@@ -470,6 +540,11 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                     if (++pf_ch == NC) {
                         pf_ch = 0;
                         pf_tile += unit_stride;
+                        if (pf_tile >= total_tiles) {     // next fused step: same units, q_{n-1} / q_n swapped
+                            pf_tile = unit0;
+                            ++pf_step;
+                            const float* t = pf_prev; pf_prev = pf_cur; pf_cur = t;
+                        }
                         pf_e = patch0(pf_tile) + (int64_t)row_in * BM + seg * 4;
                     }
                 }
@@ -481,7 +556,12 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
             for (int p = 0; p < EDEPTH - 1; ++p) issue();
             uint32_t src = ring + (uint32_t)lane * 4;           // consume cursor (this lane's dim column of the chunk)
             int slot = 0;
+            uint32_t sig_k = 0;                                 // tiles handed to the signaller so far
+            for (int step = 0; step < n_steps; ++step)
             for (int64_t tile = unit0; tile < total_tiles; tile += unit_stride) {
+                float* const q_out = (step & 1) ? a.q_cur : a.q_prev;            // q_{n+1} replaces q_{n-1}
+                __nv_bfloat16* const hi_out = (step & 1) ? a.q_hi_cur : a.q_hi_next;
+                __nv_bfloat16* const lo_out = step == n_steps - 1 ? a.q_lo_next : nullptr;
                 const int m_tile = m_tile_of(tile);
                 const int64_t n_tile = tile / m_units;
                 const int d = m_tile * BM + quarter * 32 + lane;
@@ -493,19 +573,15 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                 const int64_t cbase = n_tile * BN + half * NCH * 32;
                 // warp-uniform: every lane's dim is real and all of this warp's chains exist -> no predicates
                 const bool fast = __all_sync(0xffffffffu, d_ok && cbase + NCH * 32 <= a.C) && !no_mem;
-                float* qw = a.q_prev + patch0(tile) + lane;      // q_{n+1} replaces q_{n-1}
+                float* qw = q_out + patch0(tile) + lane;
                 const int64_t b0i = box_index(cbase, d, a.kblocks, BN);
-                __nv_bfloat16* hw = a.q_hi_next + b0i;
-                __nv_bfloat16* lw = a.q_lo_next ? a.q_lo_next + b0i : nullptr;
-                mbar_wait(tfull(acc), acc_phase);
+                __nv_bfloat16* hw = hi_out + b0i;
+                __nv_bfloat16* lw = lo_out ? lo_out + b0i : nullptr;
+                if (!(a.debug & 8)) mbar_wait(tfull(acc), acc_phase);   // debug 8 (with 1): free-running epilogue, no accumulator handshake
                 tc_fence_after();
-#pragma unroll 1
-                for (int ch = 0; ch < NC; ++ch) {
-                    issue();
-                    cp_async_wait<EDEPTH - 1>();      // this chunk has landed
-                    __syncwarp();
-                    uint32_t v[CWID];
-                    tmem_ld16(t0 + ch * CWID, v);
+                // one chunk: 16 chains x this lane's dim.  eps*r_{n+1/2} = eps*r_{n-1/2} + eps^2*m*g ;
+                // q_{n+1} = q_n + eps*r_{n+1/2}
+                auto process = [&](const uint32_t (&v)[CWID], int ch) {
                     if (fast) {
                         if (lw == nullptr) {
 #pragma unroll
@@ -514,7 +590,6 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                                 asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pj) : "r"(src + j * 128));
                                 asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qj) : "r"(src + CWID * 128 + j * 128));
                                 const float gj = cv - __uint_as_float(v[j]);
-                                // eps*r_{n+1/2} = eps*r_{n-1/2} + eps^2*m*g ;  q_{n+1} = q_n + eps*r_{n+1/2}
                                 const float qn = qj + fmaf(em2, gj, qj - pj);
                                 __stcs(qw + j * BM, qn);
                                 hw[j * BK] = __float2bfloat16_rn(qn);
@@ -555,6 +630,26 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                     src += ECHUNK_BYTES;
                     if (++slot == EDEPTH) { slot = 0; src -= EDEPTH * ECHUNK_BYTES; }
                     __syncwarp();                     // stage may be refilled by the next issue
+                };
+                // the accumulator chunk of the NEXT iteration is requested before the current one is processed
+                static_assert(NC % 2 == 0, "two register sets ping-pong");
+                uint32_t va[CWID], vb[CWID];
+                const bool no_tmem = (a.debug & 16) != 0;     // debug 16: the accumulator is never read
+                if (!no_tmem) tmem_ld16_async(t0, va);
+#pragma unroll 1
+                for (int ch = 0; ch < NC; ch += 2) {
+                    issue();
+                    cp_async_wait<EDEPTH - 1>();      // this chunk has landed
+                    __syncwarp();
+                    tmem_wait_ld16(va);
+                    if (!no_tmem) tmem_ld16_async(t0 + (ch + 1) * CWID, vb);
+                    process(va, ch);
+                    issue();
+                    cp_async_wait<EDEPTH - 1>();
+                    __syncwarp();
+                    tmem_wait_ld16(vb);
+                    if (ch + 2 < NC && !no_tmem) tmem_ld16_async(t0 + (ch + 2) * CWID, va);
+                    process(vb, ch + 1);
                 }
                 if (!d_ok && !no_mem) {   // pad dim (last dim-tile only): keep the next operand's padding zero
                     hw -= NC * CWID * BK;
@@ -567,8 +662,13 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                 }
                 tc_fence_before();
                 if constexpr (PAIR) {          // one arrival per warp on the LEADER's barrier
+                    if (step < n_steps - 1) fence_proxy_async_global();   // this lane's operand stores -> (other CTAs') TMA reads
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty(acc), 0));
+                    if (lane == 0) {
+                        if (!(a.debug & 8)) mbar_arrive_cluster(mapa_rank(tempty(acc), 0));
+                        if (step < n_steps - 1) mbar_arrive(twritten(sig_k));
+                    }
+                    ++sig_k;
                 } else {
                     mbar_arrive(tempty(acc));
                 }
@@ -832,6 +932,39 @@ static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int Dp, int b
     return BK_OK;
 }
 
+constexpr int MAX_FUSED_STEPS = 64;     // sync counters reserved in the workspace: MAX_FUSED_STEPS x n_tiles
+
+// How many leapfrog steps one persistent STEP launch may fuse: needs the pair kernel with EVERY cluster of the
+// grid co-resident (the producers spin on counters other clusters advance).  1 = launch per step.
+// BK_TC_FUSE=0 (diagnostic) forces 1.
+static int max_fused_steps(int m_tiles, int debug) {
+    static int fuse_env = -1, pair_env = -1, clusters = -1, sms = 0;
+    if (fuse_env < 0) { const char* e = getenv("BK_TC_FUSE"); fuse_env = (e && e[0] == '0') ? 0 : 1; }
+    if (pair_env < 0) { const char* e = getenv("BK_TC_PAIR"); pair_env = (e && e[0] == '0') ? 0 : 1; }
+    if (!fuse_env || !pair_env || m_tiles % 2 != 0 || (debug & 4)) return 1;
+    if (clusters < 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1;
+        cudaFuncSetAttribute(k_dense_tc<TC_MODE_STEP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Cfg<TC_MODE_STEP, true>::SMEM_BYTES);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2u * (unsigned)(sms / 2));
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = Cfg<TC_MODE_STEP, true>::SMEM_BYTES;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, k_dense_tc<TC_MODE_STEP, true>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+        clusters = n;
+    }
+    return clusters >= sms / 2 ? MAX_FUSED_STEPS : 1;
+}
+
 static int launch_tc(const Model& m, const StepArgs& a, const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo,
                      cudaStream_t st) {
     static bool attr = false;
@@ -850,7 +983,7 @@ static int launch_tc(const Model& m, const StepArgs& a, const __nv_bfloat16* b_h
     // half of the chain tile -- needs an even number of dim-tiles; BK_TC_PAIR=0 selects the single-CTA kernel
     static int pair_env = -1;
     if (pair_env < 0) { const char* e = getenv("BK_TC_PAIR"); pair_env = (e && e[0] == '0') ? 0 : 1; }
-    const bool pair = pair_env && a.m_tiles % 2 == 0 && !(a.debug & 5);
+    const bool pair = pair_env && a.m_tiles % 2 == 0 && !(a.debug & 4);
     static int sms = 0;
     if (!sms) {
         int dev = 0;
@@ -864,7 +997,10 @@ static int launch_tc(const Model& m, const StepArgs& a, const __nv_bfloat16* b_h
     if ((rc = make_map(&mA1, m.P_lo, m.Dp, (int)m.Dp, BM, bk))) return rc;
     const int brows = pair ? BN / 2 : BN;      // pair: each CTA loads half of a stored 256-row box
     if ((rc = make_map(&mB0, b_hi, a.C, (int)m.Dp, brows, bk, BN))) return rc;
-    if ((rc = make_map(&mB1, b_lo ? b_lo : b_hi, a.C, (int)m.Dp, brows, bk, BN))) return rc;
+    // fused steps: the operand buffers alternate -- mapB0 = read by even steps, mapB1 = read by odd steps
+    const __nv_bfloat16* b1 = a.n_steps > 1 ? a.q_hi_next : (b_lo ? b_lo : b_hi);
+    if ((rc = make_map(&mB1, b1, a.C, (int)m.Dp, brows, bk, BN))) return rc;
+    if (a.n_steps > 1 && !(pair && a.mode == TC_MODE_STEP)) { set_error("fused steps need the pair STEP kernel"); return BK_E_INVALID; }
     const int tag = a.mode == TC_MODE_STEP ? BK_PROF_STEP : BK_PROF_GRAD;
     if (pair) {
         const int64_t units = a.n_tiles * (a.m_tiles / 2);
@@ -880,6 +1016,8 @@ static int launch_tc(const Model& m, const StepArgs& a, const __nv_bfloat16* b_h
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
+        if (a.n_steps > 1)
+            BK_CUDA(cudaMemsetAsync(a.sync, 0, (size_t)(a.n_steps - 1) * a.n_tiles * sizeof(uint32_t), st));
         prof_begin(tag, st);
         cudaError_t e;
         if (a.mode == TC_MODE_STEP) {
@@ -953,8 +1091,9 @@ size_t dense_tc_hmc_ws_bytes(const Model& m, int64_t C) {
     const size_t n = (size_t)align_up((size_t)C, tc::BN) * m.Dp;   // tile-blocked, padded
     const size_t nb = n;                                           // box-blocked bf16, padded
     // q, r, gq fp32; h0; q_hi x2, q_lo bf16; eval scratch for the cache refresh
+    const size_t n_tiles = align_up((size_t)C, tc::BN) / tc::BN;
     return 3 * align_up(n * 4, 256) + align_up((size_t)C * 4, 256) + 3 * align_up(nb * 2, 256) +
-           model_eval_ws_bytes(m, C) + 2048;
+           align_up(tc::MAX_FUSED_STEPS * n_tiles * 4, 256) + model_eval_ws_bytes(m, C) + 2048;
 }
 
 // gradient of the dense plugin on tensor cores (3-pass split): theta [C,D] -> grad [C,D]
@@ -988,6 +1127,7 @@ int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* 
     float* h0 = ar.take<float>(C);
     __nv_bfloat16* qhi[2] = {ar.take<__nv_bfloat16>(nb), ar.take<__nv_bfloat16>(nb)};
     __nv_bfloat16* qlo = ar.take<__nv_bfloat16>(nb);
+    uint32_t* sync = ar.take<uint32_t>(tc::MAX_FUSED_STEPS * (align_up((size_t)C, tc::BN) / tc::BN));
     const size_t ebytes = model_eval_ws_bytes(m, C);
     void* ews = ar.take<char>(ebytes);
     if (!ar.ok()) {
@@ -1028,16 +1168,23 @@ int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* 
         else tc::k_hmc_begin_tc<false><<<wblocks, 256, 0, st>>>(h, t, L == 1 ? 1 : 0);
         BK_LAUNCH_CHECK();
         int cur = 0;
-        for (int s = 1; s < L; ++s) {   // fused gradient + kick + drift, bf16 operands
+        const int max_fuse = tc::max_fused_steps(a.m_tiles, a.debug);
+        for (int s = 1; s < L;) {   // fused gradient + kick + drift, bf16 operands; up to max_fuse steps per launch
+            const int ns = (L - s) < max_fuse ? (L - s) : max_fuse;
             a.mode = TC_MODE_STEP; a.n_pass = 1;
-            a.q_hi_next = qhi[cur ^ 1];
-            a.q_lo_next = (s == L - 1) ? qlo : nullptr;
-            a.q_prev = h.qm; a.q_cur = h.q;         // q_{s+1} overwrites q_{s-1}
+            a.n_steps = ns; a.sync = sync;
+            a.q_hi_next = qhi[cur ^ 1]; a.q_hi_cur = qhi[cur];
+            a.q_lo_next = (s + ns == L) ? qlo : nullptr;   // the last step's operand also gets its low half
+            a.q_prev = h.qm; a.q_cur = h.q;         // q_{s+1} overwrites q_{s-1}; roles swap every step
             rc = tc::launch_tc(m, a, qhi[cur], nullptr, st);
             if (rc) return rc;
-            cur ^= 1;
-            float* t2 = h.qm; h.qm = h.q; h.q = t2;
+            if (ns & 1) {
+                cur ^= 1;
+                float* t2 = h.qm; h.qm = h.q; h.q = t2;
+            }
+            s += ns;
         }
+        a.n_steps = 1;
         // endpoint gradient with the 3-pass split: enters the Hamiltonian and the cache
         a.mode = TC_MODE_GRAD; a.n_pass = 3; a.q_hi_next = nullptr; a.q_lo_next = nullptr;
         rc = tc::launch_tc(m, a, qhi[cur], qlo, st);

@@ -181,7 +181,7 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return run_reference_arm(args)
-    for v in ("BK_TC_DEBUG", "BK_DISABLE_TC", "BK_FORCE_GENERIC", "BK_HLR_DEBUG", "BK_ESS", "BK_ACF"):   # diagnostic switches of the library
+    for v in ("BK_TC_DEBUG", "BK_DISABLE_TC", "BK_FORCE_GENERIC", "BK_HLR_DEBUG", "BK_ESS", "BK_ACF", "BK_LIB", "BK_TC_FUSE", "BK_TC_PAIR"):   # diagnostic switches of the library
         if os.environ.get(v, "0") not in ("", "0"):
             raise SystemExit(f"{v} is set: refusing to benchmark a diagnostic configuration")
 
@@ -301,15 +301,20 @@ def main():
     peak_bw = peaks.get("hbm_gbs") or 6650.0               # fallback: B200_PROFILING.md
     peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-    bytes_per_launch = 4.0 * D * 4 * C                      # 16 KB per chain-leapfrog-step
+    # one persistent STEP launch fuses the interior leapfrog steps of a draw (L-1 of them at c2); algorithmic
+    # bytes per launch = 16 B per chain-dim-step x the steps that launch ran
+    steps_per_launch = (L - 1) * args.steps / max(sn.value, 1)
+    bytes_per_launch = 4.0 * D * 4 * C * steps_per_launch   # 16 KB per chain-leapfrog-step
     s_avg_ms = sms_.value / max(sn.value, 1)
     g_avg_ms = gms.value / max(gn.value, 1)
     achieved = bytes_per_launch / (s_avg_ms * 1e-3) / 1e9 if sn.value else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_bw, "unit": "GB/s",
                 "frac": (achieved / peak_bw) if achieved else None,
                 # ncu --set full, profiles/: dram read+write per STEP launch (incl. the bf16 operand copy)
-                "traffic": 1.034e9 if C == CHAINS_PER_GPU else None,
-                "kernel": "k_dense_tc STEP mode (tcgen05 gradient GEMM + fused leapfrog epilogue)",
+                "traffic": 1.034e9 * steps_per_launch if C == CHAINS_PER_GPU else None,
+                "kernel": "k_dense_tc STEP mode (tcgen05 gradient GEMM + fused leapfrog epilogue, "
+                          "persistent over the interior leapfrog steps of a draw)",
+                "leapfrog_steps_per_launch": steps_per_launch,
                 "launches_timed": int(sn.value), "avg_launch_ms": s_avg_ms,
                 "share_of_step": sms_.value / ms if ms else None, "peak_source": peak_src,
                 "tensor_side": {  # the endpoint gradient (3-pass bf16 split) is tensor-bound
