@@ -140,7 +140,7 @@ class ChainSampler:
     def reset_moments(self) -> None:
         self._mom = None
 
-    def sample_host(self, theta_host=None, out=None, chunk_chains: Optional[int] = None):
+    def sample_host(self, theta_host=None, out=None, chunk_chains=None):
         """One draw of every chain with HOST buffers, pipelined over chain chunks.
 
         The reference's ``sample()`` hands back host arrays (hmc.py:63); this is
@@ -170,11 +170,20 @@ class ChainSampler:
             if t is not None and (tuple(t.shape) != shape or t.dtype != self.dtype or t.is_cuda
                                   or not t.is_contiguous()):
                 raise ValueError(f"{name} must be a contiguous host {self.dtype} tensor of shape {shape}")
-        if chunk_chains is None:
-            # 37 chain-tiles of 256 (two full waves of the 148-CTA gradient GEMM) at D ~ 1000
-            chunk_chains = max(256, int(round(9472 * 1000 / max(D, 1) / 256)) * 256)
-        chunk_chains = max(1, min(int(chunk_chains), C_))
-        sizes = [min(chunk_chains, C_ - c) for c in range(0, C_, chunk_chains)]
+        if isinstance(chunk_chains, (list, tuple)):     # explicit chunk sizes
+            sizes = [int(c) for c in chunk_chains]
+            if any(c <= 0 for c in sizes) or sum(sizes) != C_:
+                raise ValueError(f"chunk sizes must be positive and sum to {C_}")
+        else:
+            if chunk_chains is None:
+                # 37 chain-tiles of 256 (two full waves of the 148-CTA gradient GEMM) at D ~ 1000
+                chunk_chains = max(256, int(round(9472 * 1000 / max(D, 1) / 256)) * 256)
+            chunk_chains = max(1, min(int(chunk_chains), C_))
+            sizes = []
+            c = sum(sizes)
+            while c < C_:
+                sizes.append(min(chunk_chains, C_ - c))
+                c += sizes[-1]
         if getattr(self, "_hs", None) is None:
             self._hs = tuple(torch.cuda.Stream(self.device) for _ in range(3))
             self._h_draw = torch.empty(C_, D, dtype=self.dtype, device=self.device)

@@ -272,7 +272,7 @@ struct StepArgs {
     float* g_out;         // [C, D] row-major, or tile-blocked when g_blocked
     int g_blocked;
     int debug;            // BK_TC_DEBUG bits: 1 = skip TMA+MMA, 2 = skip epilogue global traffic, 4 = load B on even stages only,
-                          // 8 (with 1) = no accumulator handshake (free-running epilogue), 16 = accumulator never read
+                          // 16 = accumulator never read
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -403,7 +403,6 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         // ================= MMA issuer (one thread) =================
         if (PAIR && rank != 0) {
             // the peer CTA's MMA warp only took part in the TMEM allocation
-        } else if (lane == 0 && (a.debug & 8)) {   // experiment: nothing to hand over
         } else if (lane == 0 && (a.debug & 1)) {   // experiment: no GEMM, just hand the accumulators over
             int acc = 0;
             uint32_t acc_phase = 0;
@@ -577,7 +576,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                 const int64_t b0i = box_index(cbase, d, a.kblocks, BN);
                 __nv_bfloat16* hw = hi_out + b0i;
                 __nv_bfloat16* lw = lo_out ? lo_out + b0i : nullptr;
-                if (!(a.debug & 8)) mbar_wait(tfull(acc), acc_phase);   // debug 8 (with 1): free-running epilogue, no accumulator handshake
+                mbar_wait(tfull(acc), acc_phase);
                 tc_fence_after();
                 // one chunk: 16 chains x this lane's dim.  eps*r_{n+1/2} = eps*r_{n-1/2} + eps^2*m*g ;
                 // q_{n+1} = q_n + eps*r_{n+1/2}
@@ -665,7 +664,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                     if (step < n_steps - 1) fence_proxy_async_global();   // this lane's operand stores -> (other CTAs') TMA reads
                     __syncwarp();
                     if (lane == 0) {
-                        if (!(a.debug & 8)) mbar_arrive_cluster(mapa_rank(tempty(acc), 0));
+                        mbar_arrive_cluster(mapa_rank(tempty(acc), 0));
                         if (step < n_steps - 1) mbar_arrive(twritten(sig_k));
                     }
                     ++sig_k;

@@ -28,7 +28,7 @@ def _mk(bk, kind, C, seed):
 
 
 @pytest.mark.parametrize("kind", ["hmc_dense", "hmc_iso", "mala_dense", "mala_iso", "metropolis"])
-@pytest.mark.parametrize("C,chunk", [(1000, 256), (777, 300), (512, None)])
+@pytest.mark.parametrize("C,chunk", [(1000, 256), (777, 300), (512, None), (1000, [256, 500, 244])])
 def test_sample_host_equals_device_sample(bk, kind, C, chunk):
     a, b = _mk(bk, kind, C, 11), _mk(bk, kind, C, 11)
     host_in = a.theta.cpu().pin_memory()
