@@ -195,24 +195,42 @@ class ChainSampler:
             s.wait_stream(cur)
         # state loaded from the host (or never evaluated): the (logp, grad) cache is stale
         stale = theta_host is not None or not self._cache_valid.value
+        # optional timeline (scripts/e2e_sweep.py): self._trace = [] collects (stream, chunk, start, end) events
+        trace = getattr(self, "_trace", None)
+
+        def mark(stream):
+            if trace is None:
+                return None
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            return e
         c0 = 0
-        for cn in sizes:
+        for k, cn in enumerate(sizes):
             valid = L.i32(0 if stale else 1)
             if theta_host is not None:
                 with torch.cuda.stream(s_in):
+                    t0 = mark(s_in)
                     self._theta[c0:c0 + cn].copy_(theta_host[c0:c0 + cn], non_blocking=True)
+                    if trace is not None:
+                        trace.append(("h2d", k, t0, mark(s_in)))
                 s_run.wait_stream(s_in)
             with torch.cuda.stream(s_run):
                 rng = make_rng(self._seed, self._t, self._chain_offset + c0, None, None, self._n_uniform)
                 o = L.DrawOut(self._h_draw[c0:].data_ptr(), self._h_logp[c0:].data_ptr(),
                               self._h_acc[c0:].data_ptr())
+                t0 = mark(s_run)
                 self._launch(1, rng, o, c0, cn, valid)
-                done = torch.cuda.Event()
+                done = torch.cuda.Event(enable_timing=trace is not None)
                 done.record(s_run)
+                if trace is not None:
+                    trace.append(("run", k, t0, done))
             s_out.wait_event(done)
             with torch.cuda.stream(s_out):
+                t0 = mark(s_out)
                 draw_h[c0:c0 + cn].copy_(self._h_draw[c0:c0 + cn], non_blocking=True)
                 logp_h[c0:c0 + cn].copy_(self._h_logp[c0:c0 + cn], non_blocking=True)
+                if trace is not None:
+                    trace.append(("d2h", k, t0, mark(s_out)))
             c0 += cn
         self._t += 1
         self.last_accept = self._h_acc

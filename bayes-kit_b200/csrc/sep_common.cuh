@@ -26,6 +26,7 @@ struct Lanes {
     int lane;   // lane within group
     int D;
     bool vec;
+    bool vec2 = false;   // fp32, D even, rows 8-byte aligned (e.g. D = 50): 64-bit accesses, two per element block
     __device__ __forceinline__ int elem(int k) const { return 4 * (lane + G * (k >> 2)) + (k & 3); }
     __device__ __forceinline__ bool valid(int k) const { return elem(k) < D; }
 
@@ -41,6 +42,16 @@ struct Lanes {
                     double2 a = *reinterpret_cast<const double2*>(row + e0);
                     double2 b = *reinterpret_cast<const double2*>(row + e0 + 2);
                     v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = b.x; v[4 * j + 3] = b.y;
+                }
+            } else if (sizeof(T) == 4 && vec2) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (e0 + 2 * h + 1 < D) {
+                        const float2 t = *reinterpret_cast<const float2*>(row + e0 + 2 * h);
+                        v[4 * j + 2 * h] = t.x; v[4 * j + 2 * h + 1] = t.y;
+                    } else {
+                        v[4 * j + 2 * h] = fill; v[4 * j + 2 * h + 1] = fill;
+                    }
                 }
             } else {
 #pragma unroll
@@ -60,6 +71,11 @@ struct Lanes {
                     *reinterpret_cast<double2*>(row + e0) = make_double2(v[4 * j], v[4 * j + 1]);
                     *reinterpret_cast<double2*>(row + e0 + 2) = make_double2(v[4 * j + 2], v[4 * j + 3]);
                 }
+            } else if (sizeof(T) == 4 && vec2) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (e0 + 2 * h + 1 < D)
+                        *reinterpret_cast<float2*>(row + e0 + 2 * h) = make_float2(v[4 * j + 2 * h], v[4 * j + 2 * h + 1]);
             } else {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)

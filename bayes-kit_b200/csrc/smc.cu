@@ -16,7 +16,7 @@ struct SmcArgs {
     const T* src;              // particles to move: row src_idx[m] (the pending resample) or row m
     const int64_t* src_idx;    // [M] or NULL
     int64_t M;
-    int D, vec;
+    int D, vec, vec2;
     const T *mu, *pl, *m0, *p0;
     T t0, t1, scale;
     bk_rng rng;
@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(128) k_smc_move_weight(SmcArgs<T> a) {
     ln.lane = threadIdx.x % G;
     ln.D = a.D;
     ln.vec = a.vec != 0;
+    ln.vec2 = a.vec2 != 0;
     T mu[NE], pl[NE], m0[NE], p0[NE];
     ln.load(a.mu, mu, T(0));
     ln.load(a.pl, pl, T(0));
@@ -151,6 +152,10 @@ static int smc_move_t(const Model& m, const void* src, const int64_t* src_idx, v
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     a.vec = (a.D % 4 == 0 && al(thetas) && al(src) && al(a.mu) && al(a.pl) && al(a.m0) && al(a.p0) &&
              (rng->mode != BK_RNG_INJECTED || al(rng->normals))) ? 1 : 0;
+    auto al8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; };
+    // D even but not a multiple of 4 (c4: D = 50): rows are 8-byte aligned -> 64-bit accesses
+    a.vec2 = (!a.vec && sizeof(T) == 4 && a.D % 2 == 0 && al8(thetas) && al8(src) && al8(a.mu) && al8(a.pl) &&
+              al8(a.m0) && al8(a.p0) && (rng->mode != BK_RNG_INJECTED || al8(rng->normals))) ? 1 : 0;
     const int D = a.D;
     if (D <= 4) return launch_smc<T, 1, 1>(a, st);
     if (D <= 16) return launch_smc<T, 4, 1>(a, st);

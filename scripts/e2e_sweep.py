@@ -15,11 +15,22 @@ def ramp(*head, full):
     while sum(sizes) < C:
         sizes.append(min(full, C - sum(sizes)))
     return sizes
-layouts = {"9472": 9472, "13056": 13056, "16384": 16384, "21760": 21760, "32768": 32768,
-           "ramp 2304,4608 + 9472": ramp(2304, 4608, full=9472),
-           "ramp 4096,8192 + 16384": ramp(4096, 8192, full=16384),
-           "ramp 2048,4096,8192 + 16384": ramp(2048, 4096, 8192, full=16384),
-           "ramp 4096,8192,16384 + 32768 (tail 4352)": [4096, 8192, 16384, 32512, 4352]}
+def both(up, full):
+    """ramp-up chunks, full chunks, mirrored ramp-down; the remainder joins the middle"""
+    down = list(reversed(up))
+    mid = C - sum(up) - sum(down)
+    n = max(1, round(mid / full))
+    base = (mid // n) // 256 * 256
+    mids = [base] * n
+    mids[n // 2] += mid - base * n
+    return list(up) + mids + down
+layouts = {"9472": 9472,
+           "ramp-up 2304,4608 + 9472": ramp(2304, 4608, full=9472),
+           "both 2304,4608 | 9472": both([2304, 4608], 9472),
+           "both 1280,2304,4864 | 9472": both([1280, 2304, 4864], 9472),
+           "both 1024,2048,4096 | 8192": both([1024, 2048, 4096], 8192),
+           "both 768,1536,3072,6144 | 12288": both([768, 1536, 3072, 6144], 12288),
+           "both 512,1024,2048,4096 | 8192": both([512, 1024, 2048, 4096], 8192)}
 for name, ch in layouts.items():
     for _ in range(2):
         s.sample_host(bufs[0], out=(bufs[1], lp), chunk_chains=ch)
@@ -30,3 +41,13 @@ for name, ch in layouts.items():
         s.sample_host(bufs[i % 2], out=(bufs[(i + 1) % 2], lp), chunk_chains=ch)
     dt = (time.perf_counter() - t0) / n
     print(f"{name:45s} {dt * 1e3:6.2f} ms/step  {C / dt / 1e6:6.2f} M chain-steps/s", flush=True)
+
+# timeline of one step with the default layout: start / end of every chunk's copy-in, kernels and copy-out (ms from
+# the first event), from CUDA events recorded on the three streams
+s._trace = []
+s.sample_host(bufs[0], out=(bufs[1], lp))
+torch.cuda.synchronize()
+ref = min((t for t in s._trace if t[0] == "h2d"), key=lambda t: t[1])[2]
+for kind in ("h2d", "run", "d2h"):
+    print(kind, " ".join(f"[{ref.elapsed_time(a):.2f}-{ref.elapsed_time(b):.2f}]" for k, _, a, b in s._trace if k == kind))
+s._trace = None
