@@ -1011,20 +1011,15 @@ static int launch_tc(const Model& m, const StepArgs& a, const __nv_bfloat16* b_h
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(THREADS);
         cfg.stream = st;
-        cudaLaunchAttribute at[2];
+        cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        // fused steps spin on counters other clusters advance: a cooperative launch makes the driver start the
-        // grid only when ALL of it is resident (also next to kernels of other streams); if this driver refuses
-        // the cooperative + cluster combination the plain launch is used (the occupancy query already passed)
-        static int coop = 1;
-        if (a.n_steps > 1 && coop) {
-            at[1].id = cudaLaunchAttributeCooperative;
-            at[1].val.cooperative = 1;
-            cfg.numAttrs = 2;
-        }
+        // (A cooperative launch would make the driver guarantee the fused grid's co-residency next to kernels of
+        // other streams too, but Nsight Compute cannot replay a cooperative cluster launch -- "LaunchFailed" --
+        // so co-residency rests on the occupancy query in max_fused_steps(); do not run two fused launches
+        // concurrently on one device.)
         if (a.n_steps > 1)
             BK_CUDA(cudaMemsetAsync(a.sync, 0, (size_t)(a.n_steps - 1) * a.n_tiles * sizeof(uint32_t), st));
         prof_begin(tag, st);
@@ -1032,13 +1027,7 @@ static int launch_tc(const Model& m, const StepArgs& a, const __nv_bfloat16* b_h
         if (a.mode == TC_MODE_STEP) {
             cfg.dynamicSmemBytes = Cfg<TC_MODE_STEP, true>::SMEM_BYTES;
             e = cudaLaunchKernelEx(&cfg, k_dense_tc<TC_MODE_STEP, true>, mA0, mA1, mB0, mB1, a);
-            if (e != cudaSuccess && cfg.numAttrs == 2) {     // cooperative + cluster refused: plain launch from now on
-                fprintf(stderr, "bk: cooperative cluster launch refused (%s); using the plain launch\n", cudaGetErrorString(e));
-                cudaGetLastError();
-                coop = 0;
-                cfg.numAttrs = 1;
-                e = cudaLaunchKernelEx(&cfg, k_dense_tc<TC_MODE_STEP, true>, mA0, mA1, mB0, mB1, a);
-            }
+
         } else {
             cfg.dynamicSmemBytes = Cfg<TC_MODE_GRAD, true>::SMEM_BYTES;
             e = cudaLaunchKernelEx(&cfg, k_dense_tc<TC_MODE_GRAD, true>, mA0, mA1, mB0, mB1, a);
