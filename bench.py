@@ -310,8 +310,9 @@ def main():
     achieved = bytes_per_launch / (s_avg_ms * 1e-3) / 1e9 if sn.value else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_bw, "unit": "GB/s",
                 "frac": (achieved / peak_bw) if achieved else None,
-                # ncu --set full, profiles/: dram read+write per STEP launch (incl. the bf16 operand copy)
-                "traffic": 1.034e9 * steps_per_launch if C == CHAINS_PER_GPU else None,
+                # ncu --set full (profiles/r1_ncu_k_dense_tc.md): dram read + write of one fused launch = 9.81 GB for
+                # 9 leapfrog steps (incl. the bf16 operand copy and the pad dims 1000..1023) = 1.090 GB per step
+                "traffic": 1.090e9 * steps_per_launch if C == CHAINS_PER_GPU else None,
                 "kernel": "k_dense_tc STEP mode (tcgen05 gradient GEMM + fused leapfrog epilogue, "
                           "persistent over the interior leapfrog steps of a draw)",
                 "leapfrog_steps_per_launch": steps_per_launch,
