@@ -6,6 +6,8 @@
 // test are evaluated in-kernel; only the draw (+ logp, accept flag) goes to HBM.
 //
 // Reference semantics: hmc.py:36-63, mala.py:40-79, metropolis.py:12-135.
+#include <stdlib.h>
+
 #include "sampler_sep.h"
 
 namespace bk {
@@ -188,12 +190,23 @@ static int launch_gj(const SepArgs<T>& a, cudaStream_t st) {
     return BK_OK;
 }
 
+// BK_SEP_WIDE=0 (diagnostic): one element block per lane for every D
+static bool wide_groups() {
+    static int w = -1;
+    if (w < 0) { const char* e = getenv("BK_SEP_WIDE"); w = (e && e[0] == '0') ? 0 : 1; }
+    return w != 0;
+}
+
 template <typename T, int MK>
 static int launch_mk(const SepArgs<T>& a, cudaStream_t st) {
     const int D = a.D;
     if (D <= 4) return launch_gj<T, 1, 1, MK>(a, st);
     if (D <= 16) return launch_gj<T, 4, 1, MK>(a, st);
     if (D <= 32) return launch_gj<T, 8, 1, MK>(a, st);
+    // fp32 (timed mode): fewer lanes per chain with 16 elements each -- the per-lane overhead of a draw (Philox
+    // set-up, reductions, accept, addressing) is paid by 8 lanes instead of 32.  G * J is unchanged, so the
+    // Philox blocks and the accept-uniform rule (spare block G * J - 1) are the same as for the <32, 1> layout.
+    if (sizeof(T) == 4 && D > 64 && D <= 128 && wide_groups()) return launch_gj<T, 8, 4, MK>(a, st);
     if (D <= 64) return launch_gj<T, 16, 1, MK>(a, st);
     if (D <= 128) return launch_gj<T, 32, 1, MK>(a, st);
     if (D <= 256) return launch_gj<T, 32, 2, MK>(a, st);

@@ -5,6 +5,8 @@
 //   bk_smc_resample_indices  -- normalise, block scan -> CDF, binary search
 //                               (multinomial = np.random.choice; systematic)
 //   bk_gather_rows           -- thetas[idx]
+#include <stdlib.h>
+
 #include "model.h"
 #include "sep_common.cuh"
 
@@ -124,7 +126,7 @@ template <typename T, int G, int J>
 static int launch_smc(const SmcArgs<T>& a, cudaStream_t st) {
     const int64_t per_block = 128 / G;
     const int64_t need = (a.M + per_block - 1) / per_block;
-    const int64_t cap = 148 * 8;                      // persistent: 8 CTAs of 128 threads per SM (62 registers)
+    const int64_t cap = 148 * (J >= 4 ? 4 : 8);       // persistent: 8 CTAs of 128 threads per SM (62 registers), 4 for 16 elements per lane
     k_smc_move_weight<T, G, J><<<(unsigned)(need < cap ? need : cap), 128, 0, st>>>(a);
     BK_LAUNCH_CHECK();
     return BK_OK;
@@ -160,6 +162,11 @@ static int smc_move_t(const Model& m, const void* src, const int64_t* src_idx, v
     if (D <= 4) return launch_smc<T, 1, 1>(a, st);
     if (D <= 16) return launch_smc<T, 4, 1>(a, st);
     if (D <= 32) return launch_smc<T, 8, 1>(a, st);
+    // fp32 (timed mode): 4 lanes x 16 elements instead of 16 x 4 -- the per-lane overhead of a particle visit is
+    // paid by a quarter of the lanes; G * J (Philox blocks, spare-block uniform rule) is unchanged.  BK_SEP_WIDE=0: off
+    static int wide = -1;
+    if (wide < 0) { const char* e = getenv("BK_SEP_WIDE"); wide = (e && e[0] == '0') ? 0 : 1; }
+    if (sizeof(T) == 4 && wide && D > 32 && D <= 64) return launch_smc<T, 4, 4>(a, st);
     if (D <= 64) return launch_smc<T, 16, 1>(a, st);
     if (D <= 128) return launch_smc<T, 32, 1>(a, st);
     if (D <= 256) return launch_smc<T, 32, 2>(a, st);
