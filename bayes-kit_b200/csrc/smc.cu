@@ -126,7 +126,19 @@ template <typename T, int G, int J>
 static int launch_smc(const SmcArgs<T>& a, cudaStream_t st) {
     const int64_t per_block = 128 / G;
     const int64_t need = (a.M + per_block - 1) / per_block;
-    const int64_t cap = 148 * (J >= 4 ? 4 : 8);       // persistent: 8 CTAs of 128 threads per SM (62 registers), 4 for 16 elements per lane
+    // persistent: exactly one wave -- as many CTAs of 128 threads as are resident at once (8 per SM at 62
+    // registers, 3 for the 16-elements-per-lane layout)
+    static int64_t cap = 0;
+    if (!cap) {
+        int dev = 0, sms = 148, nb = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_smc_move_weight<T, G, J>, 128, 0) != cudaSuccess || nb < 1) {
+            cudaGetLastError();
+            nb = 1;
+        }
+        cap = (int64_t)sms * (nb > 8 ? 8 : nb);
+    }
     k_smc_move_weight<T, G, J><<<(unsigned)(need < cap ? need : cap), 128, 0, st>>>(a);
     BK_LAUNCH_CHECK();
     return BK_OK;
