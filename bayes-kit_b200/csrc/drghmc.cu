@@ -11,6 +11,7 @@
 // The reference's (logp, grad) cache stack (drghmc.py:82,243-247) only avoids
 // recomputation: a deterministic plugin returns identical values, so the
 // kernel recomputes log p and its gradient from the position.
+#include <stdlib.h>
 #include "model.h"
 #include "sep_common.cuh"
 
@@ -238,6 +239,10 @@ static int launch_dr_mk(const DrArgs<T>& a, cudaStream_t st) {
     if (D <= 4) return launch_dr<T, 1, 1, MK>(a, st);
     if (D <= 16) return launch_dr<T, 4, 1, MK>(a, st);
     if (D <= 32) return launch_dr<T, 8, 1, MK>(a, st);
+    // fp32: 8 lanes x 16 elements per chain (see sampler_sep.cu: same Philox blocks, a quarter of the per-lane overhead)
+    static int wide = -1;
+    if (wide < 0) { const char* e = getenv("BK_SEP_WIDE"); wide = (e && e[0] == '0') ? 0 : 1; }
+    if (sizeof(T) == 4 && wide && D > 64 && D <= 128) return launch_dr<T, 8, 4, MK>(a, st);
     if (D <= 64) return launch_dr<T, 16, 1, MK>(a, st);
     if (D <= 128) return launch_dr<T, 32, 1, MK>(a, st);
     if (D <= 256) return launch_dr<T, 32, 2, MK>(a, st);
