@@ -155,6 +155,9 @@ class ChainSampler:
                     recomputed); None keeps the device-resident state.
         out         (draw_host [C, D], logp_host [C]) pinned tensors to fill;
                     allocated (pinned) when None.
+        chunk_chains  chains per chunk (default: 37 chain-tiles of 256 at D ~ 1000) or an explicit
+                    list of chunk sizes summing to C.  Setting ``self._trace = []`` beforehand
+                    collects (stream, chunk, start, end) CUDA events of the three streams.
         Returns (draw_host, logp_host), complete on return; ``theta`` holds the
         same draw on device and ``last_accept`` the accept flags.
         """

@@ -55,6 +55,10 @@ def test_sample_host_validates(bk):
     with pytest.raises(ValueError):
         s.sample_host(torch.zeros(64, 100, dtype=torch.float64))
     with pytest.raises(ValueError):
+        s.sample_host(chunk_chains=[32, 16])          # explicit chunk sizes must cover every chain exactly once
+    with pytest.raises(ValueError):
+        s.sample_host(chunk_chains=[64, 0])
+    with pytest.raises(ValueError):
         bk.HMCDiag(bk.IsoGauss(5), 0.1, 3).sample_host()
     d = bk.DrGhmcDiag(bk.IsoGauss(5), 2, [0.2, 0.1], [2, 4], 0.5, chains=8, seed=0)
     with pytest.raises(NotImplementedError):
