@@ -243,6 +243,7 @@ static int launch_dr_mk(const DrArgs<T>& a, cudaStream_t st) {
     static int wide = -1;
     if (wide < 0) { const char* e = getenv("BK_SEP_WIDE"); wide = (e && e[0] == '0') ? 0 : 1; }
     if (sizeof(T) == 4 && wide && D > 64 && D <= 128) return launch_dr<T, 8, 4, MK>(a, st);
+    if (sizeof(T) == 4 && wide && D > 32 && D <= 64) return launch_dr<T, 4, 4, MK>(a, st);
     if (D <= 64) return launch_dr<T, 16, 1, MK>(a, st);
     if (D <= 128) return launch_dr<T, 32, 1, MK>(a, st);
     if (D <= 256) return launch_dr<T, 32, 2, MK>(a, st);

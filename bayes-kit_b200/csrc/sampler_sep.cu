@@ -207,6 +207,7 @@ static int launch_mk(const SepArgs<T>& a, cudaStream_t st) {
     // set-up, reductions, accept, addressing) is paid by 8 lanes instead of 32.  G * J is unchanged, so the
     // Philox blocks and the accept-uniform rule (spare block G * J - 1) are the same as for the <32, 1> layout.
     if (sizeof(T) == 4 && D > 64 && D <= 128 && wide_groups()) return launch_gj<T, 8, 4, MK>(a, st);
+    if (sizeof(T) == 4 && D > 32 && D <= 64 && wide_groups()) return launch_gj<T, 4, 4, MK>(a, st);
     if (D <= 64) return launch_gj<T, 16, 1, MK>(a, st);
     if (D <= 128) return launch_gj<T, 32, 1, MK>(a, st);
     if (D <= 256) return launch_gj<T, 32, 2, MK>(a, st);
