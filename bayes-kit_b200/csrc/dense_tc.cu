@@ -31,6 +31,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "dense_tc.h"
 #include "sep_common.cuh"
 
@@ -1018,15 +1020,29 @@ static int launch_tc(const Model& m, const StepArgs& a, const __nv_bfloat16* b_h
         cfg.numAttrs = 1;
         // (A cooperative launch would make the driver guarantee the fused grid's co-residency next to kernels of
         // other streams too, but Nsight Compute cannot replay a cooperative cluster launch -- "LaunchFailed" --
-        // so co-residency rests on the occupancy query in max_fused_steps(); do not run two fused launches
-        // concurrently on one device.)
-        if (a.n_steps > 1)
+        // so co-residency rests on the occupancy query in max_fused_steps().)  Two fused grids that were
+        // only partly resident next to each other would wait on each other forever, so fused launches of
+        // this process never overlap: each one first waits (on its own stream, asynchronously) for the event
+        // recorded behind the previous fused launch of the device, whatever stream that ran on.  Other
+        // kernels may overlap freely -- they finish on their own and free their SMs.
+        static std::mutex fused_mu;
+        static cudaEvent_t fused_ev[64] = {nullptr};
+        std::unique_lock<std::mutex> fused_lock(fused_mu, std::defer_lock);
+        int fused_dev = -1;
+        if (a.n_steps > 1) {
+            fused_lock.lock();
+            BK_CUDA(cudaGetDevice(&fused_dev));
+            if (fused_dev < 0 || fused_dev >= 64) { set_error("device index %d out of range", fused_dev); return BK_E_CUDA; }
+            if (!fused_ev[fused_dev]) BK_CUDA(cudaEventCreateWithFlags(&fused_ev[fused_dev], cudaEventDisableTiming));
+            else BK_CUDA(cudaStreamWaitEvent(st, fused_ev[fused_dev], 0));
             BK_CUDA(cudaMemsetAsync(a.sync, 0, (size_t)(a.n_steps - 1) * a.n_tiles * sizeof(uint32_t), st));
+        }
         prof_begin(tag, st);
         cudaError_t e;
         if (a.mode == TC_MODE_STEP) {
             cfg.dynamicSmemBytes = Cfg<TC_MODE_STEP, true>::SMEM_BYTES;
             e = cudaLaunchKernelEx(&cfg, k_dense_tc<TC_MODE_STEP, true>, mA0, mA1, mB0, mB1, a);
+            if (fused_dev >= 0 && e == cudaSuccess) e = cudaEventRecord(fused_ev[fused_dev], st);
 
         } else {
             cfg.dynamicSmemBytes = Cfg<TC_MODE_GRAD, true>::SMEM_BYTES;
