@@ -118,3 +118,20 @@ def test_no_cuda_is_a_loud_error():
         bk.IsoGauss(3)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         bk.ess(np.arange(10.0))
+
+
+def test_bench_refuses_every_diagnostic_switch():
+    """Every environment switch the library reads (getenv in csrc/, BK_LIB in _lib.py) is a diagnostic configuration
+    bench.py must refuse to measure."""
+    import glob
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    switches = {"BK_LIB"}
+    for f in glob.glob(os.path.join(root, "bayes-kit_b200", "csrc", "*.cu")):
+        switches |= set(re.findall(r'getenv\("(BK_[A-Z0-9_]+)"\)', open(f).read()))
+    bench = open(os.path.join(root, "bench.py")).read()
+    assert len(switches) >= 9
+    for s in sorted(switches):
+        assert f'"{s}"' in bench, f"bench.py does not refuse {s}"
