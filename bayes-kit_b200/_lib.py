@@ -13,7 +13,9 @@ LIB_PATH = os.environ.get("BK_LIB") or os.path.join(_HERE, "libbk_b200.so")   # 
 
 BK_OK, BK_E_INVALID, BK_E_UNSUPPORTED, BK_E_CUDA, BK_E_WORKSPACE, BK_E_HANDLE = 0, -1, -2, -3, -4, -5
 BK_F32, BK_F64 = 0, 1
-MODEL_ISO, MODEL_DIAG, MODEL_DENSE, MODEL_HLR, MODEL_GPL = range(5)
+MODEL_ISO, MODEL_DIAG, MODEL_DENSE, MODEL_HLR, MODEL_GPL, MODEL_BINOM = range(6)
+SMC_KERNEL_RW, SMC_KERNEL_MALA, SMC_KERNEL_HMC = 0, 1, 2
+SMC_MAX_WORLD, SMC_MAILBOX_BYTES = 16, 4096
 RNG_PHILOX, RNG_INJECTED = 0, 1
 RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC = 0, 1
 IAT_IPSE, IAT_IMSE = 0, 1
@@ -25,12 +27,22 @@ vp, i32, i64, u64, f64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_d
 class ModelDesc(C.Structure):
     _fields_ = [("kind", i32), ("dtype", i32), ("dims", i64), ("sigma", f64), ("mu", vp),
                 ("prec", vp), ("P", vp), ("m0", vp), ("p0", vp), ("X", vp), ("y", vp),
-                ("n_obs", i64)]
+                ("n_obs", i64), ("scalars", f64 * 8)]
 
 
 class Rng(C.Structure):
     _fields_ = [("mode", i32), ("n_uniform", i32), ("seed", u64), ("draw_offset", u64),
                 ("chain_offset", u64), ("normals", vp), ("uniforms", vp)]
+
+
+class SmcKernel(C.Structure):
+    _fields_ = [("kind", i32), ("steps", i32), ("scale", f64)]
+
+
+class SmcShard(C.Structure):
+    _fields_ = [("rank", i32), ("world", i32), ("M", i64), ("epoch", u64),
+                ("particles", (vp * SMC_MAX_WORLD) * 2), ("logw", vp * SMC_MAX_WORLD),
+                ("idx", vp * SMC_MAX_WORLD), ("mailbox", vp * SMC_MAX_WORLD)]
 
 
 class DrawOut(C.Structure):
@@ -85,6 +97,11 @@ _SIGNATURES = {
     "bk_smc_resample_indices_dev": (C.c_int, [vp, i64, i32, i32, vp, vp, C.POINTER(Rng), i64, i64, vp, vp,
                                               vp, sz, vp]),
     "bk_gather_rows": (C.c_int, [vp, vp, i64, i64, i32, vp, vp]),
+    "bk_smc_shard_workspace_bytes": (sz, [i64, i32, i32]),
+    "bk_smc_shard_move": (C.c_int, [u64, C.POINTER(SmcShard), vp, i32, i32, C.POINTER(SmcKernel), C.POINTER(Rng), i32,
+                                    vp, vp, sz, vp]),
+    "bk_smc_shard_resample": (C.c_int, [C.POINTER(SmcShard), i32, i32, vp, C.POINTER(Rng), f64, i32, vp, vp, sz, vp]),
+    "bk_smc_shard_gather": (C.c_int, [C.POINTER(SmcShard), i64, i32, vp, vp]),
     "bk_rank_normalize_workspace_bytes": (sz, [i64, i32]),
     "bk_rank_normalize": (C.c_int, [vp, i32, C.POINTER(SeriesLayout), vp, vp, vp, sz, vp]),
     "bk_autocorr_workspace_bytes": (sz, [i64, i64]),

@@ -90,6 +90,28 @@ __global__ void k_prior_lik(const T* __restrict__ theta, int64_t C, int D, const
     }
 }
 
+// ---- beta-binomial on the logit scale (test/models/binomial.py:11-74), D = 1: one thread per chain
+// p = inv_logit(theta); ll = log C(N,x) + x log p + (N-x) log(1-p); prior (with the logit Jacobian) =
+// alpha log p + beta log(1-p) - log B(alpha, beta).  The gradient is analytic (the reference's test
+// model differentiates numerically).
+template <typename T>
+__global__ void k_binom_eval(const T* __restrict__ theta, int64_t C, T al, T be, T xs, T Nn, T lch, T lbe,
+                             T* __restrict__ lp, T* __restrict__ grad, T* __restrict__ lprior, T* __restrict__ llik) {
+    using A = Ar<T>;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const T th = theta[c];
+    const T e = A::exp_(-fabs(th)), l = A::log1p_(e);
+    const T lp1 = th >= T(0) ? -l : A::sub(th, l), l1m = th >= T(0) ? A::sub(-th, l) : -l;
+    const T p = th >= T(0) ? T(1) / A::add(T(1), e) : e / A::add(T(1), e);
+    const T ll = A::add(A::add(lch, A::mul(xs, lp1)), A::mul(A::sub(Nn, xs), l1m));
+    const T pr = A::sub(A::add(A::mul(al, lp1), A::mul(be, l1m)), lbe);
+    if (lp) lp[c] = A::add(ll, pr);                                  // binomial.py:34-42
+    if (grad) grad[c] = A::add(A::sub(xs, A::mul(Nn, p)), A::sub(al, A::mul(A::add(al, be), p)));
+    if (lprior) lprior[c] = pr;
+    if (llik) llik[c] = ll;
+}
+
 // ---- dense precision Gaussian on CUDA cores ----------------------------------
 // out[c, j] = -sum_k (theta[c,k] - mu[k]) P[k, j]   (P symmetric, row-major)
 // 64x64 tile, 16-wide k slabs, 256 threads, 4x4 micro-tile.
@@ -226,6 +248,13 @@ static int eval_t(const Model& m, const T* theta, int64_t C, T* lp, T* grad, voi
         }
         case BK_MODEL_HIER_LOGREG:
             return hlr_eval(m, theta, C, lp, grad, ws, ws_bytes, st, precise);
+        case BK_MODEL_BINOMIAL_LOGIT: {
+            const double* q = m.d.scalars;
+            k_binom_eval<T><<<(unsigned)((C + 255) / 256), 256, 0, st>>>(theta, C, (T)q[0], (T)q[1], (T)q[2], (T)q[3], (T)q[4],
+                                                                        (T)q[5], lp, grad, (T*)nullptr, (T*)nullptr);
+            BK_LAUNCH_CHECK();
+            return BK_OK;
+        }
         default:
             set_error("model kind %d has no device evaluator", m.d.kind);
             return BK_E_UNSUPPORTED;
@@ -286,6 +315,11 @@ int bk_model_create(const bk_model_desc* desc, void* ws, size_t ws_bytes, void* 
         case BK_MODEL_HIER_LOGREG:
             BK_CHECK_ARG(desc->X && desc->y && desc->n_obs > 0, "HIER_LOGREG: X, y, n_obs required");
             BK_CHECK_ARG(desc->dims >= 3, "HIER_LOGREG: dims = Dx + 2 must be >= 3");
+            break;
+        case BK_MODEL_BINOMIAL_LOGIT:
+            BK_CHECK_ARG(desc->dims == 1, "BINOMIAL_LOGIT: dims must be 1");
+            BK_CHECK_ARG(desc->scalars[0] > 0 && desc->scalars[1] > 0, "BINOMIAL_LOGIT: alpha, beta must be > 0");
+            BK_CHECK_ARG(desc->scalars[3] >= desc->scalars[2] && desc->scalars[2] >= 0, "BINOMIAL_LOGIT: need 0 <= x <= N");
             break;
         default:
             set_error("bk_model_create: unknown kind %d", desc->kind);
@@ -348,12 +382,25 @@ int bk_model_log_prior_likelihood(uint64_t handle, const void* theta, int64_t C,
                                   void* log_prior_out, void* log_lik_out, void* stream) {
     const Model* m = get_model(handle);
     if (!m) return BK_E_HANDLE;
-    BK_CHECK_ARG(m->d.kind == BK_MODEL_GAUSS_PRIOR_LIK,
-                 "log_prior/log_likelihood need a GAUSS_PRIOR_LIK model");
+    BK_CHECK_ARG(m->d.kind == BK_MODEL_GAUSS_PRIOR_LIK || m->d.kind == BK_MODEL_BINOMIAL_LOGIT,
+                 "log_prior/log_likelihood need a GAUSS_PRIOR_LIK or BINOMIAL_LOGIT model");
     if (C == 0) return BK_OK;
     const int D = (int)m->d.dims;
     const unsigned blocks = (unsigned)((C * 32 + 255) / 256);
     cudaStream_t st = (cudaStream_t)stream;
+    if (m->d.kind == BK_MODEL_BINOMIAL_LOGIT) {
+        const double* q = m->d.scalars;
+        const unsigned bb = (unsigned)((C + 255) / 256);
+        if (m->d.dtype == BK_F64)
+            k_binom_eval<double><<<bb, 256, 0, st>>>((const double*)theta, C, q[0], q[1], q[2], q[3], q[4], q[5], nullptr,
+                                                      nullptr, (double*)log_prior_out, (double*)log_lik_out);
+        else
+            k_binom_eval<float><<<bb, 256, 0, st>>>((const float*)theta, C, (float)q[0], (float)q[1], (float)q[2], (float)q[3],
+                                                     (float)q[4], (float)q[5], nullptr, nullptr, (float*)log_prior_out,
+                                                     (float*)log_lik_out);
+        BK_LAUNCH_CHECK();
+        return BK_OK;
+    }
     if (m->d.dtype == BK_F64)
         k_prior_lik<double><<<blocks, 256, 0, st>>>((const double*)theta, C, D, (const double*)m->d.mu,
                                                      (const double*)m->d.prec, (const double*)m->d.m0,

@@ -59,3 +59,15 @@ def all_reduce_logsumexp(local_max: torch.Tensor, local_sumexp: torch.Tensor, gr
     s = local_sumexp * torch.exp(local_max - gmax)
     dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
     return gmax, s
+
+
+def shared_seed(seed: int, group=None, device=None) -> int:
+    """``seed=None`` resolves to fresh entropy on every rank; the ranks of one sampler must share the
+    Philox key, so rank 0's value is broadcast (one-off, at construction)."""
+    rank, world = rank_world(group)
+    if world == 1:
+        return seed
+    t = torch.tensor([seed & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64,
+                     device=device if dist.get_backend(group) == "nccl" else "cpu")
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return int(t.item())

@@ -39,6 +39,8 @@ class DeviceModel:
         d.kind, d.dtype, d.dims = self._kind, dtype_id(self.dtype), self._dims
         d.sigma = float(fields.pop("sigma", 1.0))
         d.n_obs = int(fields.pop("n_obs", 0))
+        for i, v in enumerate(fields.pop("scalars", ())):
+            d.scalars[i] = float(v)
         for k, t in fields.items():
             if t is not None:
                 self._keep.append(t)
@@ -172,6 +174,38 @@ class GaussPriorLik(DeviceModel):
         return self._pl(theta, "lik")
 
 
+class Binomial(DeviceModel):
+    """Beta-binomial on the logit scale -- the reference's own test target
+    (test/models/binomial.py:11-74): ``theta = logit(p)``, ``x ~ Binomial(N, p)``,
+    ``p ~ Beta(alpha, beta)`` with the logit Jacobian; ``log_prior`` / ``log_likelihood`` for the SMC
+    (binomial.py:44-54), analytic gradient (the reference differentiates numerically)."""
+
+    _kind = L.MODEL_BINOM
+
+    def __init__(self, alpha, beta, x, N, dtype=torch.float32, device="cuda"):
+        import math
+        super().__init__(1, dtype, device)
+        self.alpha, self.beta, self.x, self.N = float(alpha), float(beta), int(x), int(N)
+        lch = math.lgamma(N + 1) - math.lgamma(x + 1) - math.lgamma(N - x + 1)
+        lbe = math.lgamma(alpha) + math.lgamma(beta) - math.lgamma(alpha + beta)
+        self._register(scalars=(alpha, beta, x, N, lch, lbe))
+
+    _pl = GaussPriorLik._pl
+    log_prior = GaussPriorLik.log_prior
+    log_likelihood = GaussPriorLik.log_likelihood
+
+    def constrain_draws(self, draws):      # binomial.py:67-68
+        return torch.sigmoid(draws)
+
+    def posterior_mean(self) -> float:     # binomial.py:70-74
+        a, b = self.alpha + self.x, self.beta + self.N - self.x
+        return a / (a + b)
+
+    def posterior_variance(self) -> float:
+        a, b = self.alpha + self.x, self.beta + self.N - self.x
+        return a * b / ((a + b) ** 2 * (a + b + 1))
+
+
 class HierLogReg(DeviceModel):
     """Hierarchical logistic regression (BASELINE config c3; density in DESIGN.md)."""
 
@@ -190,6 +224,6 @@ def require_plugin(model) -> DeviceModel:
         raise TypeError(
             "bayes_kit_b200 samplers evaluate the model inside CUDA kernels: `model` must be a "
             "registered device plugin (bayes_kit_b200.models.IsoGauss / DiagGauss / DensePrecGauss / "
-            "HierLogReg / GaussPriorLik), not an arbitrary Python object. Python callbacks cannot "
+            "HierLogReg / GaussPriorLik / Binomial), not an arbitrary Python object. Python callbacks cannot "
             f"run per step on the device and there is no CPU fallback (got {type(model).__name__}).")
     return model

@@ -1,10 +1,16 @@
 """TemperedLikelihoodSMC (reference: bayes_kit/smc.py).
 
 All M particles move, reweight and resample on device, one temperature per
-``transition(n)``: a fused RW-Metropolis move + log-weight kernel, a block-scan
-CDF + binary-search resampler and a row gather.  Particles shard across ranks;
-the only communication is the naturally global resampling step (all-gather of
-log-weights and particles over NCCL), see dist.py.
+``transition(n)``: a fused move + log-weight kernel (random-walk Metropolis as in
+the reference, or a MALA / HMC transition -- the TODO of smc.py:78), a single-pass
+fixed-point scan and a resolve kernel -- three launches per temperature.
+
+Particles shard across the GPUs of a box (one process per GPU).  No host-side
+collective runs per temperature and no particle array is exchanged: the ranks post
+three small messages per step into each other's mailboxes (local max of the
+log-weights, local weight mass, "indices final"), store the resample indices of the
+offspring they resolve straight into the owner's index array, and the next move
+reads the selected rows from their owners over NVLink peer memory (peer.py, bk.h).
 """
 from __future__ import annotations
 
@@ -13,68 +19,117 @@ from typing import Iterator, Optional
 
 import numpy as np
 import torch
+import torch.distributed as dist
 
 from . import _lib as L
 from . import dist as D_
-from ._util import Workspace, make_rng, ptr, resolve_seed, stream_ptr, to_dev
-from .models import GaussPriorLik, require_plugin
+from . import peer as P_
+from ._util import make_rng, resolve_seed, stream_ptr, to_dev
+from .models import Binomial, GaussPriorLik, require_plugin
 
 
-class RWMetropolisKernel:
+class _Kernel:
+    kind = L.SMC_KERNEL_RW
+    steps = 0
+
+    def __init__(self, scale: float, what: str = "scale"):
+        self.scale = float(scale)
+        if not self.scale > 0:
+            raise ValueError(f"{what} must be positive, got {scale}")
+
+    def desc(self) -> L.SmcKernel:
+        return L.SmcKernel(self.kind, self.steps, self.scale)
+
+
+class RWMetropolisKernel(_Kernel):
     """Device descriptor returned by ``metropolis_kernel(scale)``: one
     random-walk Metropolis move ``theta* = normal(loc=theta, scale)`` accepted
     iff ``log(u) < lp(theta*) - lp(theta)`` (smc.py:79-89)."""
 
-    def __init__(self, scale: float):
-        self.scale = float(scale)
-        if not self.scale > 0:
-            raise ValueError(f"scale must be positive, got {scale}")
+
+class MALAKernel(_Kernel):
+    """One MALA transition (mala.py:40-66) on the tempered density ``lp_t = ll * t + prior``."""
+    kind = L.SMC_KERNEL_MALA
+
+    def __init__(self, epsilon: float):
+        super().__init__(epsilon, "epsilon")
+
+
+class HMCKernel(_Kernel):
+    """One HMCDiag transition (hmc.py:40-63, identity metric) on the tempered density."""
+    kind = L.SMC_KERNEL_HMC
+
+    def __init__(self, stepsize: float, steps: int):
+        super().__init__(stepsize, "stepsize")
+        self.steps = int(steps)
+        if self.steps < 0:
+            raise ValueError(f"steps must be >= 0, got {steps}")
 
 
 def metropolis_kernel(scale: float) -> RWMetropolisKernel:
     return RWMetropolisKernel(scale)
 
 
+def mala_kernel(epsilon: float) -> MALAKernel:
+    """MCMC-kernel plug-in for the SMC (the TODO at smc.py:78)."""
+    return MALAKernel(epsilon)
+
+
+def hmc_kernel(stepsize: float, steps: int) -> HMCKernel:
+    """MCMC-kernel plug-in for the SMC (the TODO at smc.py:78)."""
+    return HMCKernel(stepsize, steps)
+
+
 class TemperedLikelihoodSMC:
     """``TemperedLikelihoodSMC(model, M, N, sample_initial, kernel)`` (smc.py:13-27).
 
-    * ``model``: a ``GaussPriorLik`` plugin (``log_prior`` / ``log_likelihood``).
+    * ``model``: a plugin with ``log_prior`` / ``log_likelihood`` (``GaussPriorLik``, ``Binomial``).
     * ``sample_initial``: the reference's callable ``m -> theta0[m]`` (evaluated
       once per particle on the host, as smc.py:23 does), or directly an [M, D]
       array / tensor.
-    * ``kernel``: ``metropolis_kernel(scale)``.
+    * ``kernel``: ``metropolis_kernel(scale)`` (the reference's), ``mala_kernel(eps)``, ``hmc_kernel(eps, L)``.
     * ``resample``: ``"multinomial"`` (reference semantics: no max-shift, legacy
       ``np.random.choice`` indices) or ``"systematic"`` (log-sum-exp normalised,
-      stratified points; north_star item 2).
+      stratified points, exact fixed-point CDF: the indices do not depend on how the
+      particles are sharded; north_star item 2).
     * ``ess_threshold``: None (the reference: resample at every temperature,
       smc.py:60) or a fraction in (0, 1]: resample only when the importance-weight
       ESS drops below ``ess_threshold * M``, carrying the log-weights otherwise
       (``log_weights``, ``resampled``); the decision is taken on device.
-    With torch.distributed initialised, M is the GLOBAL particle count and each
-    rank owns a contiguous slice.
+    With torch.distributed initialised (or ``group=`` given), M is the GLOBAL particle
+    count and each rank owns a contiguous slice.
     """
 
     def __init__(self, model, M: int, N: int, sample_initial, kernel, *, resample: str = "multinomial",
                  ess_threshold: Optional[float] = None, seed=None, group=None):
         self._model = require_plugin(model)
-        if not isinstance(self._model, GaussPriorLik):
+        if not isinstance(self._model, (GaussPriorLik, Binomial)):
             raise TypeError("TemperedLikelihoodSMC needs a model plugin with log_prior/log_likelihood "
-                            "(bayes_kit_b200.models.GaussPriorLik)")
-        if not isinstance(kernel, RWMetropolisKernel):
-            raise TypeError("kernel must be bayes_kit_b200.metropolis_kernel(scale): arbitrary Python "
-                            "kernels cannot run per particle on the GPU and there is no CPU fallback")
+                            "(bayes_kit_b200.models.GaussPriorLik / Binomial)")
+        if not isinstance(kernel, _Kernel):
+            raise TypeError("kernel must be bayes_kit_b200.metropolis_kernel(scale) (or mala_kernel / hmc_kernel): "
+                            "arbitrary Python kernels cannot run per particle on the GPU and there is no CPU fallback")
         if resample not in ("multinomial", "systematic"):
             raise ValueError("resample must be 'multinomial' or 'systematic'")
         if ess_threshold is not None and not 0 < ess_threshold <= 1:
             raise ValueError(f"ess_threshold must be in (0, 1], got {ess_threshold}")
+        if ess_threshold is not None and resample != "systematic":
+            raise ValueError("ess_threshold needs resample='systematic'")
         self.ess_threshold = ess_threshold      # None: resample at every temperature (smc.py:60)
         self.M, self.N = int(M), int(N)
         self.kernel = kernel
         self.resample = resample
+        self._mode = L.RESAMPLE_MULTINOMIAL if resample == "multinomial" else L.RESAMPLE_SYSTEMATIC
         self.device, self.dtype = self._model.device, self._model.dtype
-        self._seed = resolve_seed(seed)
+        self._dt = L.BK_F32 if self.dtype == torch.float32 else L.BK_F64
         self._group = group
-        self._rank, self._world = D_.rank_world(group)
+        self._rank, self._world = P_.rank_world(group)
+        if self._world > L.SMC_MAX_WORLD:
+            raise ValueError(f"at most {L.SMC_MAX_WORLD} ranks")
+        if self.M < self._world:
+            raise ValueError("need at least one particle per rank")
+        self._seed = D_.shared_seed(resolve_seed(seed), None if isinstance(group, P_.FakeRank) else group,
+                                    self.device) if seed is None else resolve_seed(seed)
         self._lo, self._hi = D_.shard_range(self.M, self._rank, self._world)
         if callable(sample_initial):
             th = np.array([np.asarray(sample_initial(m), dtype=np.float64)
@@ -84,17 +139,52 @@ class TemperedLikelihoodSMC:
             th = sample_initial
             if th.shape[0] == self.M and self._world > 1:
                 th = th[self._lo:self._hi]
-        self._thetas = to_dev(th, self.dtype, self.device).clone()
-        self._pending = None   # (all-gathered particles, resample indices) not yet materialised
-        self.D = self._thetas.shape[1]
+        self._src_local = to_dev(th, self.dtype, self.device).clone()   # particles the next move starts from
+        self._pending = False   # True: the current particles are rows idx[m] of the step's arrays (not materialised)
+        self.D = self._src_local.shape[1]
         if self.D != self._model.dims():
             raise ValueError("sample_initial returned the wrong dimension")
-        self._ws = Workspace(self.device)
-        self.last_indices = None
+        if self._src_local.shape[0] != self._hi - self._lo:
+            raise ValueError("sample_initial returned the wrong number of particles")
+        # ---- peer-addressable state: two particle arrays, log-weights, indices, mailbox ----------
+        es = 4 if self.dtype == torch.float32 else 8
+        n_max = -(-self.M // self._world)
+        key = f"smc{id(self) if not isinstance(group, P_.FakeRank) else ''}:{self.M}:{self.D}:{es}"
+        self._mem = P_.PeerRegion(key, {"p0": n_max * self.D * es, "p1": n_max * self.D * es, "logw": n_max * es,
+                                        "idx": n_max * 8, "mail": L.SMC_MAILBOX_BYTES}, self.device, group)
+        nl = self._hi - self._lo
+        self._parts = [self._mem.tensor("p0", self.dtype, (nl, self.D)), self._mem.tensor("p1", self.dtype, (nl, self.D))]
+        self._logw = self._mem.tensor("logw", self.dtype, (nl,))
+        self._idx = self._mem.tensor("idx", torch.int64, (nl,))
+        self._mail = self._mem.tensor("mail", torch.int64, (L.SMC_MAILBOX_BYTES // 8,))
+        self._ws = torch.zeros(int(L.lib().bk_smc_shard_workspace_bytes(self.M, self._world, self._mode)),
+                               dtype=torch.uint8, device=self.device)
+        self._stats = torch.zeros(self.N + 1, 4, dtype=torch.float64, device=self.device)
+        self._epoch = 0
+        self._steps_taken = []
+        self._shard = None
         self.last_accept = None
-        self._stats_log = []  # per temperature: device tensor [shift, sum w, sum w^2]
-        self._logw_acc = None  # adaptive resampling: log-weights carried between temperatures
-        self._resampled_log = []
+
+    # ---- plumbing --------------------------------------------------------------------
+    def _sh(self) -> L.SmcShard:
+        if self._shard is None:
+            s = L.SmcShard()
+            s.rank, s.world, s.M = self._rank, self._world, self.M
+            for name, field in (("p0", s.particles[0]), ("p1", s.particles[1]), ("logw", s.logw), ("idx", s.idx),
+                                ("mail", s.mailbox)):
+                for r, p in enumerate(self._mem.ptrs(name)):
+                    field[r] = p
+            self._shard = s
+        self._shard.epoch = self._epoch
+        return self._shard
+
+    def _check(self) -> None:
+        """Raise if a kernel flagged the mailbox (synchronises)."""
+        err = int(self._mail[0].item())
+        if err == 1:
+            raise L.BkError("TemperedLikelihoodSMC: a rank did not arrive within 20 s (dead peer?); the particles are invalid")
+        if err == 2:
+            raise FloatingPointError("TemperedLikelihoodSMC: every importance weight vanished")
 
     # ---- reference surface -----------------------------------------------------------
     @property
@@ -102,19 +192,18 @@ class TemperedLikelihoodSMC:
         """Current particles [M_local, D] (smc.py:23,60).  The resampling gather
         ``thetas[idxs]`` (smc.py:75) is normally folded into the next move's read;
         it is materialised here when the particles are asked for."""
-        if self._pending is not None:
-            src, idx = self._pending
-            new = torch.empty(idx.shape[0], self.D, dtype=self.dtype, device=self.device)
+        if self._pending:
+            new = torch.empty(self._hi - self._lo, self.D, dtype=self.dtype, device=self.device)
             with torch.cuda.device(self.device):
-                L.check(L.lib().bk_gather_rows(src.data_ptr(), idx.data_ptr(), idx.shape[0], self.D,
-                                               L.BK_F32 if self.dtype == torch.float32 else L.BK_F64,
-                                               new.data_ptr(), stream_ptr(self.device)))
-            self._thetas, self._pending = new, None
-        return self._thetas
+                L.check(L.lib().bk_smc_shard_gather(C.byref(self._sh()), self.D, self._dt, new.data_ptr(),
+                                                    stream_ptr(self.device)))
+            self._src_local, self._pending = new, False
+            self._check()
+        return self._src_local
 
     @thetas.setter
     def thetas(self, value) -> None:
-        self._thetas, self._pending = to_dev(value, self.dtype, self.device).clone(), None
+        self._src_local, self._pending = to_dev(value, self.dtype, self.device).clone(), False
 
     def log_prior(self, theta):
         return self._model.log_prior(theta)
@@ -129,87 +218,95 @@ class TemperedLikelihoodSMC:
     def run(self) -> None:
         for n in range(1, self.N + 1):
             self.transition(n)
+        self._check()
 
     def time(self, n: int) -> float:
         return n / self.N
 
     @property
     def weight_ess(self):
-        """Importance-weight ESS (sum w)^2 / sum w^2 per temperature taken so far.
-        Diagnostic only: the reference resamples unconditionally (smc.py:60)."""
-        if not self._stats_log:
+        """Importance-weight ESS (sum w)^2 / sum w^2 (over ALL ranks) per temperature taken so far.
+        Diagnostic only unless ``ess_threshold`` is set: the reference resamples unconditionally (smc.py:60)."""
+        if not self._steps_taken:
             return []
-        s = torch.stack(self._stats_log).cpu()
-        return [float(a * a / b) if b > 0 else float("nan") for _, a, b in s.tolist()]
+        s = self._stats[: len(self._steps_taken)].cpu()
+        return [float(a * a / b) if b > 0 else float("nan") for _, a, b, _ in s.tolist()]
 
     @property
     def log_weights(self) -> torch.Tensor:
         """Unnormalised log-weights of the current particles (zeros right after a resampling)."""
-        if self._logw_acc is None:
+        if self.ess_threshold is None or self._epoch == 0:
             return torch.zeros(self._hi - self._lo, dtype=self.dtype, device=self.device)
-        return self._logw_acc
+        return self._logw
 
     @property
     def resampled(self):
-        """Per temperature taken so far: did the adaptive rule resample?"""
-        if not self._resampled_log:
+        """Per temperature taken so far: did the step resample?"""
+        if not self._steps_taken:
             return []
-        return [bool(v) for v in torch.cat(self._resampled_log).cpu().tolist()]
+        return [bool(v) for v in self._stats[: len(self._steps_taken), 3].cpu().tolist()]
+
+    @property
+    def last_indices(self) -> Optional[torch.Tensor]:
+        """Resample indices (global particle ids) of this rank's slots after the last step.  With more than
+        one rank they are final once every rank finished the step (``thetas`` / ``run()`` wait for that)."""
+        return self._idx if self._epoch else None
 
     def transition(self, n: int, normals=None, acc_uniforms=None, res_uniforms=None) -> None:
         """One temperature step (smc.py:46-60).  The optional arrays inject the
         reference's recorded legacy-RNG streams (parity mode): proposal normals
-        [M, D], accept uniforms [M], resampling uniforms [M] (systematic: [1])."""
+        [M_local, D], accept uniforms [M_local], resampling uniforms [M_local] (systematic: [1])."""
+        self._move(n, normals, acc_uniforms)
+        self._resample(n, res_uniforms, 0)
+
+    # the two halves of a step; a FakeWorld test drives every rank through _move, then _resample(.., 1),
+    # then _resample(.., 2) so that each kernel finds its messages already posted
+    def _move(self, n: int, normals=None, acc_uniforms=None) -> None:
         lib = L.lib()
         Ml = self._hi - self._lo
-        st = stream_ptr(self.device)
-        logw = torch.empty(Ml, dtype=self.dtype, device=self.device)
-        acc = torch.empty(Ml, dtype=torch.int32, device=self.device)
+        self._epoch += 1
+        self._acc = torch.empty(Ml, dtype=torch.int32, device=self.device)
         if normals is not None:
             normals = to_dev(normals, self.dtype, self.device).reshape(Ml, self.D)
             acc_uniforms = to_dev(acc_uniforms, self.dtype, self.device).reshape(Ml)
+        self._inj = (normals, acc_uniforms)     # keep the injected streams alive until the kernel ran
         rng = make_rng(self._seed, n, self._lo, normals, acc_uniforms, 1)
-        mode = L.RESAMPLE_MULTINOMIAL if self.resample == "multinomial" else L.RESAMPLE_SYSTEMATIC
+        kn = self.kernel.desc()
+        src = None if self._pending else self._src_local.data_ptr()
+        accumulate = 1 if (self.ess_threshold is not None and self._epoch > 1) else 0
         with torch.cuda.device(self.device):
-            prev = None if self._logw_acc is None else self._logw_acc.data_ptr()
-            if self._pending is not None:     # move reads thetas_prev[idx]: gather + move in one pass
-                src, src_idx = self._pending
-                moved = torch.empty(Ml, self.D, dtype=self.dtype, device=self.device)
-                L.check(lib.bk_smc_gather_move_weight_acc(
-                    self._model.handle, src.data_ptr(), src_idx.data_ptr(), moved.data_ptr(), Ml, n, self.N,
-                    self.kernel.scale, C.byref(rng), prev, logw.data_ptr(), acc.data_ptr(), st))
-                self._thetas, self._pending = moved, None
-            else:
-                L.check(lib.bk_smc_gather_move_weight_acc(
-                    self._model.handle, self._thetas.data_ptr(), None, self._thetas.data_ptr(), Ml, n, self.N,
-                    self.kernel.scale, C.byref(rng), prev, logw.data_ptr(), acc.data_ptr(), st))
-            # --- the naturally global step: normaliser + resampling ---------------------
-            logw_all = D_.all_gather_cat(logw, self._group)      # [M]
-            thetas_all = D_.all_gather_cat(self._thetas, self._group)  # [M, D]
-            Mg = logw_all.shape[0]
-            wp, wn = self._ws.get(lib.bk_smc_resample_workspace_bytes(Mg))
-            stats = torch.empty(3, dtype=torch.float64, device=self.device)
-            L.check(lib.bk_smc_weight_stats(logw_all.data_ptr(), Mg, L.BK_F32 if self.dtype == torch.float32
-                                            else L.BK_F64, mode, stats.data_ptr(), wp, wn, st))
-            self._stats_log.append(stats)   # stays on device: no host sync per temperature
-            if res_uniforms is not None:
-                ru = to_dev(res_uniforms, self.dtype, self.device).reshape(-1)
-                if mode == L.RESAMPLE_MULTINOMIAL and ru.numel() == Mg and self._world > 1:
-                    ru = ru[self._lo:self._hi].contiguous()
-            else:
-                ru = None
-            idx = torch.empty(Ml, dtype=torch.int64, device=self.device)
-            rrng = make_rng(self._seed, n, 0)
-            L.check(lib.bk_smc_resample_indices_dev(
-                logw_all.data_ptr(), Mg, L.BK_F32 if self.dtype == torch.float32 else L.BK_F64, mode,
-                stats.data_ptr(), ptr(ru), C.byref(rrng), Ml, self._lo, idx.data_ptr(), None, wp, wn, st))
-            if self.ess_threshold is not None:
-                flag = torch.empty(1, dtype=torch.int32, device=self.device)
-                L.check(lib.bk_smc_adaptive_select(
-                    stats.data_ptr(), float(self.ess_threshold) * Mg, Ml, self._lo, idx.data_ptr(), logw.data_ptr(),
-                    L.BK_F32 if self.dtype == torch.float32 else L.BK_F64, flag.data_ptr(), st))
-                self._logw_acc = logw
-                self._resampled_log.append(flag)
-        self._pending = (thetas_all, idx)     # thetas[idxs]: folded into the next move (or .thetas)
-        self.last_indices = idx
-        self.last_accept = acc
+            L.check(lib.bk_smc_shard_move(self._model.handle, C.byref(self._sh()), src, n, self.N, C.byref(kn),
+                                          C.byref(rng), accumulate, self._acc.data_ptr(), self._ws.data_ptr(),
+                                          self._ws.numel(), stream_ptr(self.device)))
+        self.last_accept = self._acc
+
+    def _resample(self, n: int, res_uniforms=None, phase: int = 0) -> None:
+        lib = L.lib()
+        ru = None
+        if res_uniforms is not None:
+            ru = to_dev(res_uniforms, self.dtype, self.device).reshape(-1)
+            if self._mode == L.RESAMPLE_MULTINOMIAL and ru.numel() == self.M and self._world > 1:
+                ru = ru[self._lo:self._hi].contiguous()
+        self._ru = ru
+        rrng = make_rng(self._seed, n, 0)
+        thr = float(self.ess_threshold) * self.M if self.ess_threshold is not None else 0.0
+        k = len(self._steps_taken)
+        with torch.cuda.device(self.device):
+            L.check(lib.bk_smc_shard_resample(C.byref(self._sh()), self._dt, self._mode,
+                                              None if ru is None else ru.data_ptr(), C.byref(rrng), thr, phase,
+                                              self._stats[min(k, self.N)].data_ptr(), self._ws.data_ptr(),
+                                              self._ws.numel(), stream_ptr(self.device)))
+        if phase in (0, 2):
+            self._steps_taken.append(n)
+            self._pending = True    # thetas[idxs]: folded into the next move (or .thetas)
+
+    def wire_bytes_per_step(self) -> dict:
+        """Bytes this rank puts on / takes off NVLink per temperature (systematic mode), by kind: the three
+        messages to each peer, the index stores for slots other ranks own, and the particle rows read from
+        peers.  The last two depend on the weights; the figures are the expectation for exchangeable
+        particles (a fraction (G - 1) / G of a rank's offspring / parents live elsewhere)."""
+        g, nl = self._world, self._hi - self._lo
+        es = 4 if self.dtype == torch.float32 else 8
+        frac = (g - 1) / g
+        return {"messages": (16 + 32 + 8) * (g - 1), "indices": int(8 * nl * frac),
+                "particle_rows": int(nl * self.D * es * frac)}

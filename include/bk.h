@@ -52,7 +52,10 @@ enum { BK_MODEL_ISO_GAUSS = 0,        /* -0.5 |theta|^2 / sigma^2               
        BK_MODEL_DIAG_GAUSS = 1,       /* -0.5 sum prec_i (theta_i - mu_i)^2                */
        BK_MODEL_DENSE_PREC_GAUSS = 2, /* -0.5 (theta-mu)^T P (theta-mu)                    */
        BK_MODEL_HIER_LOGREG = 3,      /* hierarchical logistic regression      */
-       BK_MODEL_GAUSS_PRIOR_LIK = 4   /* prior N(m0, 1/p0) x likelihood N(mu, 1/pl) (SMC)  */ };
+       BK_MODEL_GAUSS_PRIOR_LIK = 4,  /* prior N(m0, 1/p0) x likelihood N(mu, 1/pl) (SMC)  */
+       BK_MODEL_BINOMIAL_LOGIT = 5    /* beta-binomial on the logit scale, D = 1: the reference's own
+                                         test target (test/models/binomial.py:11-74), with
+                                         log_prior / log_likelihood for the SMC                */ };
 
 enum { BK_RNG_PHILOX = 0,   /* device Philox4x32-10, counter = (block, tag, chain, draw) */
        BK_RNG_INJECTED = 1  /* pre-drawn streams in the reference's consumption order */ };
@@ -75,6 +78,7 @@ typedef struct bk_model_desc {
     const void* X;       /* [N, Dx] HIER_LOGREG design matrix                            */
     const void* y;       /* [N] HIER_LOGREG 0/1 responses                                */
     int64_t n_obs;       /* N                                                            */
+    double  scalars[8];  /* BINOMIAL_LOGIT: alpha, beta, x, N, log C(N, x), log B(alpha, beta)      */
 } bk_model_desc;
 
 typedef struct bk_rng {
@@ -130,7 +134,7 @@ BK_API int bk_model_log_density_gradient(uint64_t handle, const void* theta, int
 BK_API int bk_model_log_density_gradient_fast(uint64_t handle, const void* theta, int64_t C,
                                        void* lp_out, void* grad_out, void* ws, size_t ws_bytes,
                                        void* stream);
-/* log_prior / log_likelihood (smc.py:29-33), GAUSS_PRIOR_LIK only */
+/* log_prior / log_likelihood (smc.py:29-33): GAUSS_PRIOR_LIK, BINOMIAL_LOGIT */
 BK_API int bk_model_log_prior_likelihood(uint64_t handle, const void* theta, int64_t C,
                                   void* log_prior_out, void* log_lik_out, void* stream);
 
@@ -238,6 +242,70 @@ BK_API int bk_smc_resample_indices_dev(const void* logw, int64_t M, int32_t dtyp
 /* thetas[idxs] (smc.py:75): out [M,D] = src[idx] */
 BK_API int bk_gather_rows(const void* src, const int64_t* idx, int64_t M, int64_t D, int32_t dtype,
                    void* out, void* stream);
+
+/* ---- TemperedLikelihoodSMC sharded over G GPUs (north_star item 4) ----------------
+ * One process per GPU; rank r owns the contiguous particle range
+ *   lo(r) = r * (M / G) + min(r, M % G),  n(r) = M / G + (r < M % G).
+ * Per temperature the ranks exchange NO particle array and call NO host-side collective: the arrays
+ * below are PEER-ACCESSIBLE device memory (NVLink P2P / torch symmetric memory; with world == 1 plain
+ * device memory) and the kernels talk through them --
+ *   max message   (end of the move kernel)    local max of the log-weights            16 B per peer
+ *   mass message  (end of the scan kernel)    local fixed-point weight mass, sum w^2  32 B per peer
+ *   indices       (resolve kernel)            global particle id of every offspring,   8 B per slot
+ *                                             stored into the slot owner's idx array
+ *   done message  (end of the resolve kernel)                                          8 B per peer
+ *   particle rows (next move kernel)          row idx[m] read from its owner's array   D * s per row
+ * SYSTEMATIC resampling is defined in exact integer arithmetic so that the indices do not depend on
+ * G:  w_i = rint(exp(logw_i - max) * 2^s),  s = 61 - ceil(log2 M);  C = cumsum(w) (int64, exact);
+ * point k has threshold t_k = floor(((k + u0) / M) * W) (fp64 ops in this order, W = sum w, clamped to
+ * W - 1) and selects the first particle with C > t_k.  Rank r resolves exactly the points whose
+ * threshold falls into its own interval [O_r, O_r + W_r).  MULTINOMIAL (the reference's
+ * np.random.choice, smc.py:64-75) keeps its fp64 CDF: every rank reads all log-weights from its
+ * peers (M * s bytes) and resolves its own slots against the full CDF -- bit-identical to one GPU.
+ * All buffers are caller-owned; `ws` (bk_smc_shard_workspace_bytes) and the mailboxes must be zeroed
+ * ONCE before the first step.  A wait that is not satisfied within 20 s (dead peer) sets mailbox word
+ * 0 to 1 and the kernels finish on garbage instead of hanging; 2 = every weight vanished. */
+/* the Markov kernel that moves a particle at temperature time(n-1) (smc.py:54-57):
+ *   RW    theta* = theta + scale z, Metropolis test                       (metropolis_kernel, smc.py:79-89)
+ *   MALA  one Langevin proposal with step `scale` on the tempered density (mala.py:40-66; smc.py:78 TODO)
+ *   HMC   `steps` leapfrog steps of size `scale`, identity metric          (hmc.py:40-63;  smc.py:78 TODO) */
+enum { BK_SMC_KERNEL_RW = 0, BK_SMC_KERNEL_MALA = 1, BK_SMC_KERNEL_HMC = 2 };
+typedef struct bk_smc_kernel { int32_t kind; int32_t steps; double scale; } bk_smc_kernel;
+#define BK_SMC_MAX_WORLD 16
+#define BK_SMC_MAILBOX_BYTES 4096
+typedef struct bk_smc_shard {
+    int32_t  rank, world;
+    int64_t  M;                                   /* GLOBAL particle count                           */
+    uint64_t epoch;                               /* number of this temperature step: 1, 2, ... (the
+                                                     same on every rank)                             */
+    void*    particles[2][BK_SMC_MAX_WORLD];      /* every rank's two particle arrays [n(r), D]:
+                                                     step e writes [e & 1], reads [(e - 1) & 1]      */
+    void*    logw[BK_SMC_MAX_WORLD];              /* every rank's log-weights [n(r)]                 */
+    int64_t* idx[BK_SMC_MAX_WORLD];               /* every rank's resample indices [n(r)], global ids */
+    void*    mailbox[BK_SMC_MAX_WORLD];           /* every rank's mailbox (BK_SMC_MAILBOX_BYTES)      */
+} bk_smc_shard;
+BK_API size_t bk_smc_shard_workspace_bytes(int64_t M, int32_t world, int32_t mode);
+/* Move + weight of step n (smc.py:54-57, 67-70) for this rank's particles; the local max of the
+ * log-weights is posted to every rank from the kernel's last CTA.  Particle m starts from
+ * src_local[m] when src_local != NULL (first step, or after the caller replaced the particles),
+ * else from row idx[m] of the step-(epoch-1) arrays (peer reads) -- after waiting, in the kernel, for
+ * every rank's done message of step epoch-1.  accumulate != 0: logw += (adaptive resampling).
+ * rng->chain_offset must be lo(rank). */
+BK_API int bk_smc_shard_move(uint64_t handle, const bk_smc_shard* sh, const void* src_local, int32_t n,
+                      int32_t T, const bk_smc_kernel* kernel, const bk_rng* rng, int32_t accumulate,
+                      int32_t* accept_out, void* ws, size_t ws_bytes, void* stream);
+/* Normaliser + resampling of step `epoch`.  SYSTEMATIC: two kernels (fixed-point scan; resolve).
+ * uniforms: the injected u0 [1] (SYSTEMATIC) or this rank's [n(rank)] uniforms (MULTINOMIAL), or NULL
+ * (Philox: rng).  ess_threshold > 0 (SYSTEMATIC only): resample iff (sum w)^2 / sum w^2 <
+ * ess_threshold, else identity indices and the log-weights are kept (decided on device, identically
+ * on every rank).  stats_out (device, 4 doubles, may be NULL): max, sum exp(logw - max), sum exp(..)^2,
+ * resampled (0/1).  phase: 0 = everything; 1 / 2 = first / second kernel only (a single-GPU
+ * "fake world" test drives G ranks in lockstep on one device). */
+BK_API int bk_smc_shard_resample(const bk_smc_shard* sh, int32_t dtype, int32_t mode, const void* uniforms,
+                          const bk_rng* rng, double ess_threshold, int32_t phase, double* stats_out,
+                          void* ws, size_t ws_bytes, void* stream);
+/* thetas[idxs] (smc.py:75) materialised: out [n(rank), D] = rows idx[m] of the step-`epoch` arrays. */
+BK_API int bk_smc_shard_gather(const bk_smc_shard* sh, int64_t D, int32_t dtype, void* out, void* stream);
 
 /* ---- Stretcher: affine-invariant ensemble sampler (ensemble.py:9-66, the
  * Goodman & Weare stretch move sketched in the reference's comments) --------

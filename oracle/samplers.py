@@ -283,18 +283,35 @@ def multinomial_indices(weights, uniforms):
     return cdf.searchsorted(uniforms, side="right").astype(np.int64), cdf
 
 
+def systematic_weights(logw):
+    """Fixed-point importance weights of the systematic mode: w_i = rint(exp(logw_i - max) * 2^s) as int64,
+    s = 61 - ceil(log2 M) (so that sum w < 2^62).  Integer sums are exact and associative: the CDF, and
+    with it every resample index, is independent of how the particles are sharded over GPUs."""
+    logw = np.asarray(logw, dtype=np.float64)
+    M = logw.shape[0]
+    lg = 0
+    while (1 << lg) < M:
+        lg += 1
+    s = 61 - lg
+    e = np.exp(logw - np.max(logw))
+    e = np.where(np.isnan(e), 0.0, e)
+    return np.rint(np.ldexp(e, s)).astype(np.int64), s
+
+
 def systematic_indices(logw, u0):
     """Systematic resampling with a log-sum-exp normaliser (north_star item 2;
     NOT in the reference -- parity unpinned, this restatement is the oracle).
-    Points (i + u0)/M, i = 0..M-1, against the normalised CDF."""
-    M = logw.shape[0]
-    mx = np.max(logw)
-    w = np.exp(logw - mx)
-    cdf = np.cumsum(w)
-    cdf /= cdf[-1]
-    pts = (np.arange(M) + u0) / M
-    idx = np.searchsorted(cdf, pts, side="right")
-    return np.minimum(idx, M - 1).astype(np.int64), cdf
+    Point k has threshold t_k = floor(((k + u0) / M) * W) in fixed-point CDF units (W = sum w, fp64
+    operations in exactly this order, clamped to W - 1) and selects the first particle whose
+    inclusive integer cumsum exceeds t_k."""
+    w, _ = systematic_weights(logw)
+    M = w.shape[0]
+    cum = np.cumsum(w)
+    W = int(cum[-1])
+    t = np.floor(((np.arange(M) + u0) / M) * float(W)).astype(np.int64)
+    t = np.minimum(t, W - 1)
+    idx = np.searchsorted(cum, t, side="right")
+    return np.minimum(idx, M - 1).astype(np.int64), cum
 
 
 def smc_tempered(model, thetas0, prop_normals, acc_uniforms, res_uniforms,
@@ -441,8 +458,9 @@ def smc_tempered_adaptive(model, thetas0, prop_normals, acc_uniforms, res_unifor
             if _log_u(acc_uniforms[n - 1, m]) < lp(star, t0) - lp(thetas[m], t0):
                 thetas[m] = star
         logw = logw + np.array([lp(th, t1) - lp(th, t0) for th in thetas])
-        w = np.exp(logw - logw.max())
-        if w.sum() ** 2 / (w ** 2).sum() < ess_threshold * M:
+        wi, _ = systematic_weights(logw)          # the ESS of the fixed-point weights the resampler uses
+        wf = wi.astype(np.float64)
+        if float(int(wi.sum())) ** 2 / (wf ** 2).sum() < ess_threshold * M:
             idx, _ = systematic_indices(logw, res_uniforms[n - 1, 0])
             thetas, logw, flags[n - 1] = thetas[idx], np.zeros(M), True
     return thetas, logw, flags
