@@ -111,6 +111,8 @@ _SIGNATURES = {
     "bk_chain_moments": (C.c_int, [vp, i32, C.POINTER(SeriesLayout), vp, vp, vp]),
     "bk_moments_accumulate": (C.c_int, [vp, i32, i64, i64, i64, vp, vp, vp]),
     "bk_rhat_from_moments": (C.c_int, [vp, vp, vp, i64, i64, i64, vp, vp]),
+    "bk_rhat_partial_sums": (C.c_int, [vp, vp, i64, i64, vp, vp, vp]),
+    "bk_rhat_from_sums": (C.c_int, [vp, vp, i64, i64, vp, vp, vp]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

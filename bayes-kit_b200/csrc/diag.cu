@@ -265,6 +265,46 @@ static SeriesView view_of(const void* x, int32_t dtype, const bk_series_layout* 
                       l->draw_stride};
 }
 
+namespace bk {
+// ---- cross-rank R-hat as an all-reduce of [P, 4] sums (SURVEY 8(e) diagnostics) ---------------
+// pass 1 (ref == NULL): out[p] = {n_chains, sum_c mean_cp, sum_c var_cp}               ([P, 3])
+// pass 2 (ref = grand means after the first all-reduce): out[p] = sum_c (mean_cp - ref_p)^2   ([P])
+// One warp per parameter, chains strided over the lanes, fixed combination order.
+__global__ void k_rhat_partial(const double* __restrict__ mean, const double* __restrict__ var, int64_t n_chains,
+                               int64_t n_params, const double* __restrict__ ref, double* __restrict__ out) {
+    const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= n_params) return;
+    double s1 = 0, s2 = 0, s3 = 0;
+    const double r = ref ? ref[p] : 0.0;
+    for (int64_t c = lane; c < n_chains; c += 32) {
+        const double m = mean[c * n_params + p];
+        if (ref) { const double d = m - r; s2 += d * d; }
+        else { s1 += m; s3 += var[c * n_params + p]; }
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+    if (lane == 0) {
+        if (ref) out[p] = s2;
+        else { out[3 * p] = (double)n_chains; out[3 * p + 1] = s1; out[3 * p + 2] = s3; }
+    }
+}
+// grand mean of the chain means from the reduced sums: ref[p] = sums[p][1] / sums[p][0]
+__global__ void k_rhat_ref(const double* __restrict__ sums, int64_t n_params, double* __restrict__ ref) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n_params) ref[p] = sums[3 * p + 1] / sums[3 * p];
+}
+// rhat.py:163-170 from the reduced sums {m, sum mean, sum var} and sum (mean - gm)^2, common length N
+// (fewer than two chains in total: NaN -- the per-rank call cannot know the global count up front)
+__global__ void k_rhat_from_sums(const double* __restrict__ sums, const double* __restrict__ sqdev, int64_t n_params,
+                                 double N, double* __restrict__ out) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_params) return;
+    const double m = sums[3 * p];
+    const double var_means = sqdev[p] / (m - 1.0), mean_vars = sums[3 * p + 2] / m;
+    out[p] = m >= 2.0 ? sqrt((N - 1.0) / N + var_means / mean_vars) : nan("");
+}
+}  // namespace bk
+
 extern "C" {
 
 size_t bk_iat_ess_workspace_bytes(int32_t dtype, const bk_series_layout* layout) {
@@ -323,6 +363,33 @@ int bk_rhat_from_moments(const double* mean, const double* var, const int64_t* l
     k_rhat<<<(unsigned)((n_params * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         mean, var, lengths, N, n_chains, n_params, out);
     BK_LAUNCH_CHECK();
+    return BK_OK;
+}
+
+int bk_rhat_partial_sums(const double* mean, const double* var, int64_t n_chains, int64_t n_params,
+                         const double* ref, double* sums, void* stream) {
+    BK_CHECK_ARG(mean && sums && (ref || var) && n_chains >= 0, "bk_rhat_partial_sums: bad argument");
+    if (n_params == 0) return BK_OK;
+    k_rhat_partial<<<(unsigned)((n_params * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mean, var, n_chains,
+                                                                                           n_params, ref, sums);
+    BK_LAUNCH_CHECK();
+    return BK_OK;
+}
+
+int bk_rhat_from_sums(const double* sums, const double* sqdev, int64_t n_params, int64_t N, double* ref_out,
+                      double* out, void* stream) {
+    BK_CHECK_ARG(sums && (ref_out || (out && sqdev)), "bk_rhat_from_sums: bad argument");
+    if (n_params == 0) return BK_OK;
+    const unsigned blocks = (unsigned)((n_params + 255) / 256);
+    if (ref_out) {
+        k_rhat_ref<<<blocks, 256, 0, (cudaStream_t)stream>>>(sums, n_params, ref_out);
+        BK_LAUNCH_CHECK();
+    }
+    if (out) {
+        BK_CHECK_ARG(N >= 2, "rhat requires len(chain) >= 2 for every chain in chains");
+        k_rhat_from_sums<<<blocks, 256, 0, (cudaStream_t)stream>>>(sums, sqdev, n_params, (double)N, out);
+        BK_LAUNCH_CHECK();
+    }
     return BK_OK;
 }
 

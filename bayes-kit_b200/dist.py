@@ -1,8 +1,9 @@
 """Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL on GPUs,
 gloo in the CPU tests).  Sampling is communication-free (chains shard
 contiguously, Philox is keyed by the GLOBAL chain id); collectives appear only
-at the naturally global steps: SMC normaliser / resampling and cross-chain
-R-hat moments.
+at the naturally global steps: the Stretcher's complementary half (all-gather) and
+cross-chain R-hat moment sums (all-reduce); the sharded SMC talks through peer
+memory inside its kernels (peer.py) and calls no collective per temperature.
 """
 from __future__ import annotations
 
@@ -30,35 +31,33 @@ def shard_sizes(n: int, world: int):
     return [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
 
 
-def all_gather_cat(t: torch.Tensor, group=None) -> torch.Tensor:
-    """Concatenate every rank's tensor along dim 0 (ragged first dim allowed)."""
+def all_gather_cat(t: torch.Tensor, group=None, sizes=None) -> torch.Tensor:
+    """Concatenate every rank's tensor along dim 0.  ``sizes``: every rank's first dimension when
+    the caller knows them (shards of a known total: ``shard_sizes``) -- then nothing is exchanged
+    but the data and there is no host synchronisation; without it the sizes are all-gathered first
+    (one blocking read)."""
     rank, world = rank_world(group)
     if world == 1:
         return t
-    n_local = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-    sizes = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(sizes, n_local, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    if sizes is None:
+        n_local = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+        got = [torch.zeros_like(n_local) for _ in range(world)]
+        dist.all_gather(got, n_local, group=group)
+        sizes = [int(s.item()) for s in got]
+    sizes = [int(s) for s in sizes]
+    if sizes[rank] != t.shape[0]:
+        raise ValueError(f"all_gather_cat: rank {rank} holds {t.shape[0]} rows, sizes says {sizes[rank]}")
     mx = max(sizes)
+    if min(sizes) == mx:
+        out = torch.empty((mx * world,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+        return out
     pad = t
     if t.shape[0] < mx:
         pad = torch.cat([t, t.new_zeros((mx - t.shape[0],) + tuple(t.shape[1:]))])
     bufs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad.contiguous(), group=group)
     return torch.cat([b[:s] for b, s in zip(bufs, sizes)]).contiguous()
-
-
-def all_reduce_logsumexp(local_max: torch.Tensor, local_sumexp: torch.Tensor, group=None):
-    """Global log-normaliser pieces from per-rank (max, sum exp(x - max)):
-    returns (gmax, sum exp(x - gmax)) -- 2 scalars on the wire."""
-    rank, world = rank_world(group)
-    if world == 1:
-        return local_max, local_sumexp
-    gmax = local_max.clone()
-    dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
-    s = local_sumexp * torch.exp(local_max - gmax)
-    dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
-    return gmax, s
 
 
 def shared_seed(seed: int, group=None, device=None) -> int:

@@ -19,6 +19,7 @@ import torch
 
 from . import _lib as L
 from . import dist as D_
+from . import peer as P_
 from ._util import Workspace, make_rng, resolve_seed, stream_ptr, to_dev
 from .models import require_plugin
 
@@ -51,7 +52,7 @@ class Stretcher:
             raise ValueError(f"init must be shape of draw {self._drawshape}; found init.shape={tuple(init.shape)}")
         self._seed = resolve_seed(seed)
         self._group = group
-        self._rank, self._world = D_.rank_world(group)
+        self._rank, self._world = P_.rank_world(group)
         if init is not None:
             th = to_dev(init, self.dtype, self.device).clone()
         else:
@@ -68,6 +69,8 @@ class Stretcher:
         self._ws = Workspace(self.device)
         self._t = 0
         self.last_accept = None
+        if isinstance(group, P_.FakeRank):      # single-GPU fake world: the other ranks' halves live on this device
+            group.fake._regions.setdefault("stretch", [None] * self._world)[self._rank] = self._halves
 
     def __iter__(self):
         return self
@@ -83,26 +86,45 @@ class Stretcher:
     def sample(self, uniforms=None) -> torch.Tensor:
         """One sweep.  ``uniforms`` [walkers, 3] injects (partner, stretch, accept)
         uniforms per walker (parity mode; this rank's rows under torch.distributed)."""
+        for half in (0, 1):
+            self._half_step(half, uniforms)
+        return self.thetas
+
+    def _half_step(self, half: int, uniforms=None) -> None:
+        """Move this rank's walkers of one half against the complementary half (ensemble.py:55-63).  A
+        FakeWorld test calls this for every rank before moving on to the other half."""
         lib = L.lib()
         nl = self._hi - self._lo
         h = self._halfwalkers
-        acc = torch.empty(2, nl, dtype=torch.int32, device=self.device)
+        if half == 0:
+            self._acc = torch.empty(2, nl, dtype=torch.int32, device=self.device)
         if uniforms is not None:
             uniforms = to_dev(uniforms, self.dtype, self.device).reshape(2, nl, 3)
         with torch.cuda.device(self.device):
             wp, wn = self._ws.get(lib.bk_stretch_workspace_bytes(self._model.handle, nl))
-            for half in (0, 1):
-                other = D_.all_gather_cat(self._halves[1 - half], self._group)      # complementary walkers [h, D]
-                rng = make_rng(self._seed, 2 * self._t + half, half * h + self._lo, None, None, 3)
-                if uniforms is not None:
-                    rng.mode, rng.uniforms = L.RNG_INJECTED, uniforms[half].data_ptr()
-                L.check(lib.bk_stretch_move(
-                    self._model.handle, self._halves[half].data_ptr(), self._lp[half].data_ptr(),
-                    C.byref(self._valid[half]), other.data_ptr(), nl, other.shape[0], self._a, C.byref(rng),
-                    acc[half].data_ptr(), wp, wn, stream_ptr(self.device)))
-        self._t += 1
-        self.last_accept = acc.reshape(-1)
-        return self.thetas
+            other = self._complement(half)                                        # complementary walkers [h, D]
+            rng = make_rng(self._seed, 2 * self._t + half, half * h + self._lo, None, None, 3)
+            if uniforms is not None:
+                rng.mode, rng.uniforms = L.RNG_INJECTED, uniforms[half].data_ptr()
+            L.check(lib.bk_stretch_move(
+                self._model.handle, self._halves[half].data_ptr(), self._lp[half].data_ptr(),
+                C.byref(self._valid[half]), other.data_ptr(), nl, other.shape[0], self._a, C.byref(rng),
+                self._acc[half].data_ptr(), wp, wn, stream_ptr(self.device)))
+        if half == 1:
+            self._t += 1
+            self.last_accept = self._acc.reshape(-1)
+
+    def _complement(self, half: int) -> torch.Tensor:
+        """All walkers of the half that is NOT being moved: all-gather of every rank's slice (sizes are
+        known from the shard rule -> no size exchange, no host sync).  FakeWorld: the other ranks'
+        slices live on this device."""
+        mine = self._halves[1 - half]
+        if isinstance(self._group, P_.FakeRank):
+            reg = self._group.fake._regions["stretch"]
+            if any(r is None for r in reg):
+                raise RuntimeError("FakeWorld: construct every rank before sampling")
+            return torch.cat([r[1 - half] for r in reg])
+        return D_.all_gather_cat(mine, self._group, sizes=D_.shard_sizes(self._halfwalkers, self._world))
 
     def sample_n(self, n: int) -> torch.Tensor:
         """n sweeps -> draws [n, walkers_local, dims]."""

@@ -37,15 +37,42 @@ def _rhat_from(mean, var, lengths, N):
     return out
 
 
-def rhat(chains, device="cuda", draws_first=False, group=None):
+def _rhat_allreduce(mean, var, N, group=None, reduce_fn=None):
+    """R-hat over chains sharded across ranks: two all-reduces of [P, 2] columns of a [P, 4] sum table
+    (count + sum of chain means -> grand mean; squared deviations + sum of chain variances), i.e.
+    4 doubles per parameter on the wire in total -- never the per-chain moments (fewer than two chains
+    in total give NaN: a rank cannot know the global count before the reduce).  ``reduce_fn(t)`` replaces
+    ``dist.all_reduce`` (single-GPU "fake world" tests sum the ranks' tables on the host side)."""
+    import torch.distributed as dist
+    if reduce_fn is None:
+        def reduce_fn(t):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    lib = L.lib()
+    n_chains, n_params = mean.shape
+    mean, var = mean.contiguous(), var.contiguous()
+    f64 = dict(dtype=torch.float64, device=mean.device)
+    sums, sqdev = torch.zeros(n_params, 3, **f64), torch.zeros(n_params, **f64)
+    ref, out = torch.empty(n_params, **f64), torch.empty(n_params, **f64)
+    with torch.cuda.device(mean.device):
+        st = stream_ptr(mean.device)
+        L.check(lib.bk_rhat_partial_sums(mean.data_ptr(), var.data_ptr(), n_chains, n_params, None, sums.data_ptr(), st))
+        reduce_fn(sums)
+        L.check(lib.bk_rhat_from_sums(sums.data_ptr(), None, n_params, int(N), ref.data_ptr(), None, st))
+        L.check(lib.bk_rhat_partial_sums(mean.data_ptr(), None, n_chains, n_params, ref.data_ptr(), sqdev.data_ptr(), st))
+        reduce_fn(sqdev)
+        L.check(lib.bk_rhat_from_sums(sums.data_ptr(), sqdev.data_ptr(), n_params, int(N), None, out.data_ptr(), st))
+    return out
+
+
+def rhat(chains, device="cuda", draws_first=False, group=None, reduce_fn=None):
     """R-hat = sqrt((nbar-1)/nbar + var(chain means, ddof=1) / mean(chain vars, ddof=1)).
 
     ``chains``: the reference's list of 1-D chains (ragged allowed, returns a
     float), a ``[chains, draws]`` array (float / 0-dim tensor) or
     ``[chains, draws, params]`` (tensor [params]).  With torch.distributed
     initialised and ``group`` given (or the default group), ``chains`` is this
-    rank's shard of chains and the per-chain moments are all-gathered -- the
-    only communication.  Raises ValueError for < 2 chains or a chain with < 2
+    rank's shard of chains (all of one length) and the only communication is an
+    all-reduce of a [params, 4] table of moment sums (``_rhat_allreduce``).  Raises ValueError for < 2 chains or a chain with < 2
     draws (rhat.py:157-162)."""
     host = is_host(chains)
     ragged = (isinstance(chains, (list, tuple)) and len(chains) > 0
@@ -69,9 +96,10 @@ def rhat(chains, device="cuda", draws_first=False, group=None):
     scalar = mean.dim() <= 1
     mean = mean.reshape(mean.shape[0] if mean.dim() else 1, -1)
     var = var.reshape(mean.shape)
-    if D_.rank_world(group)[1] > 1:
-        mean, var = D_.all_gather_cat(mean, group), D_.all_gather_cat(var, group)
-    out = _rhat_from(mean, var, None, N)
+    if D_.rank_world(group)[1] > 1 or reduce_fn is not None:
+        out = _rhat_allreduce(mean, var, N, group, reduce_fn)
+    else:
+        out = _rhat_from(mean, var, None, N)
     if scalar:
         return float(out[0]) if host else out[0]
     return out

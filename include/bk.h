@@ -372,6 +372,21 @@ BK_API int bk_rhat_from_moments(const double* mean, const double* var, const int
                                 int64_t N, int64_t n_chains, int64_t n_params, double* out,
                                 void* stream);
 
+/* Cross-rank R-hat (rhat.py:163-170) when the chains are sharded over GPUs: instead of gathering
+ * per-chain moments, every rank reduces its own chains to per-parameter sums which are all-reduced
+ * (SUM) -- 4 doubles per parameter on the wire in total.  Two passes keep var(chain means) free of
+ * cancellation:
+ *   pass 1 (ref = NULL): sums [n_params, 3] = {n_chains, sum mean, sum var};  all-reduce;
+ *                        bk_rhat_from_sums(sums, NULL, .., ref_out, NULL) -> grand means [n_params]
+ *   pass 2 (ref = grand means): sqdev [n_params] = sum (mean - ref)^2;        all-reduce;
+ *                        bk_rhat_from_sums(sums, sqdev, .., NULL, out)    -> R-hat [n_params]
+ * for the common chain length N (NaN with fewer than two chains in total).  mean / var
+ * [n_chains, n_params] as written by bk_chain_moments. */
+BK_API int bk_rhat_partial_sums(const double* mean, const double* var, int64_t n_chains, int64_t n_params,
+                         const double* ref, double* out, void* stream);
+BK_API int bk_rhat_from_sums(const double* sums, const double* sqdev, int64_t n_params, int64_t N,
+                      double* ref_out, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

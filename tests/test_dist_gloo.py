@@ -1,7 +1,9 @@
-"""N>1 host logic on CPU: world_size-2 gloo processes exercise the sharding and
-the three collective call sites (SMC normaliser / resample all-gather, R-hat
-moment all-gather) of bayes_kit_b200.dist.  The oracle plays the single-process
-reference the sharded result must match."""
+"""N>1 host logic on CPU: world_size-2 gloo processes exercise the sharding rule and the
+collectives the product calls (bayes_kit_b200.dist): the Stretcher's complementary-half
+all-gather with known shard sizes, the shared-seed broadcast, and the two-pass all-reduce of
+R-hat moment sums.  (The sharded SMC uses no host-side collective: its cross-rank protocol runs
+inside the kernels and is covered by tests/test_gpu_sharded_smc.py and scripts/r2/dist_check.py.)
+The oracle plays the single-process reference the sharded result must match."""
 import os
 import socket
 
@@ -32,24 +34,30 @@ def _worker(rank, world, port, out_q):
         full = torch.arange(M * 3, dtype=torch.float64).reshape(M, 3)
         got = dist.all_gather_cat(full[lo:hi].clone())
         assert torch.equal(got, full)
-        # log-sum-exp normaliser from per-rank (max, sum exp) pairs
+        # the same gather when every rank knows the shard sizes (no size exchange, no host sync)
+        got = dist.all_gather_cat(full[lo:hi].clone(), sizes=dist.shard_sizes(M, world))
+        assert torch.equal(got, full)
+        half = torch.arange(8.0).reshape(4, 2)       # equal shards: all_gather_into_tensor path
+        l2, h2 = dist.shard_range(4, rank, world)
+        assert torch.equal(dist.all_gather_cat(half[l2:h2].clone(), sizes=dist.shard_sizes(4, world)), half)
+        # seed=None: every rank must end up with rank 0's Philox key
+        seed = dist.shared_seed(1000 + rank)
+        assert seed == 1000
+        # cross-chain R-hat as the two-pass all-reduce of per-parameter sums the product performs
+        # (rhat._rhat_allreduce: {n, sum mean, sum var} -> grand mean -> sum sq dev; 4 doubles / parameter)
         rng = np.random.default_rng(0)
-        logw = torch.as_tensor(rng.normal(size=M) * 30)
-        loc = logw[lo:hi]
-        lmax = loc.max().reshape(1)
-        lsum = torch.exp(loc - lmax).sum().reshape(1)
-        gmax, gsum = dist.all_reduce_logsumexp(lmax, lsum)
-        want = torch.logsumexp(logw, 0)
-        assert abs(float(gmax + torch.log(gsum)) - float(want)) < 1e-12
-        # cross-chain R-hat from sharded per-chain moments == oracle on all chains
-        ch = rng.normal(size=(6, 50)) + rng.normal(size=(6, 1))
-        lo, hi = dist.shard_range(6, rank, world)
-        m = torch.as_tensor(ch[lo:hi].mean(1)).reshape(-1, 1)
-        v = torch.as_tensor(ch[lo:hi].var(1, ddof=1)).reshape(-1, 1)
-        m, v = dist.all_gather_cat(m), dist.all_gather_cat(v)
-        nbar = 50.0
-        r = float(torch.sqrt((nbar - 1) / nbar + m.var(0, unbiased=True) / v.mean(0)))
-        assert abs(r - od.rhat(list(ch))) < 1e-12
+        ch = rng.normal(size=(7, 50, 3)) + 1e6 + rng.normal(size=(7, 1, 3))     # large offset: cancellation trap
+        lo, hi = dist.shard_range(7, rank, world)
+        m = torch.as_tensor(ch[lo:hi].mean(1))
+        v = torch.as_tensor(ch[lo:hi].var(1, ddof=1))
+        sums = torch.stack([torch.full((3,), float(hi - lo), dtype=torch.float64), m.sum(0), v.sum(0)], 1)
+        tdist.all_reduce(sums)
+        ref = sums[:, 1] / sums[:, 0]
+        sq = ((m - ref) ** 2).sum(0)
+        tdist.all_reduce(sq)
+        r = torch.sqrt((50.0 - 1) / 50.0 + (sq / (sums[:, 0] - 1)) / (sums[:, 2] / sums[:, 0]))
+        for p_ in range(3):
+            assert abs(float(r[p_]) - od.rhat(list(ch[:, :, p_]))) < 1e-9
         out_q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         out_q.put((rank, repr(e)))
