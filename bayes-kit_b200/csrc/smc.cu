@@ -119,7 +119,7 @@ struct BinomView {
 // processed (two dependent global loads deep), the accept uniform is drawn by the group's first lane only.
 // MOVE selects the Markov kernel applied at temperature t0 = time(n-1) (smc.py:54-57).
 template <typename T, int G, int J, template <typename, int, int> class View, int MOVE>
-__global__ void __launch_bounds__(128, (J >= 4 && sizeof(T) == 4) ? 3 : 1) k_smc_move_weight(SmcArgs<T> a) {
+__global__ void __launch_bounds__(128, (J >= 4 && sizeof(T) == 4) ? 3 : (J == 2 && G == 8) ? 5 : 1) k_smc_move_weight(SmcArgs<T> a) {
     using A = Ar<T>;
     constexpr int NE = 4 * J;
     const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / G;
@@ -369,8 +369,12 @@ static int smc_dispatch(const Model& m, SmcArgs<T>& a, const bk_smc_kernel& kn, 
     static int wide = -1;
     if (wide < 0) { const char* e = getenv("BK_SEP_WIDE"); wide = (e && e[0] == '0') ? 0 : 1; }
     if constexpr (sizeof(T) == 4) {
-        if (wide && D > 32 && D <= 64 && kn.kind == BK_SMC_KERNEL_RW)
-            return launch_smc3<T, 4, 4, GplView, BK_SMC_KERNEL_RW>(a, st);
+        static int layout = -1;   // BK_SMC_LAYOUT (diagnostic): 2 = 4 x 16 (default), 1 = 8 x 8, 0 = 16 x 4
+        if (layout < 0) { const char* e = getenv("BK_SMC_LAYOUT"); layout = e ? atoi(e) : 2; }
+        if (wide && D > 32 && D <= 64 && kn.kind == BK_SMC_KERNEL_RW) {
+            if (layout == 2) return launch_smc3<T, 4, 4, GplView, BK_SMC_KERNEL_RW>(a, st);
+            if (layout == 1) return launch_smc3<T, 8, 2, GplView, BK_SMC_KERNEL_RW>(a, st);
+        }
     }
     if (D <= 64) return launch_smc<T, 16, 1, GplView>(a, kn.kind, st);
     if (D <= 128) return launch_smc<T, 32, 1, GplView>(a, kn.kind, st);
@@ -619,17 +623,17 @@ __global__ void k_smc_adaptive_select(const double* __restrict__ stats, double t
 // cross-rank traffic through mailboxes / peer stores (smc_shard.cuh, bk.h)
 // =====================================================================================
 constexpr int SC_THREADS = 256, SC_ITEMS = 4, SC_TILE = SC_THREADS * SC_ITEMS;
-constexpr uint64_t ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_MASK = (1ull << 62) - 1;
+constexpr int RS_POINTS = 8;      // consecutive systematic points resolved per thread
 
 // control words at the head of the local workspace (zeroed once by the caller)
-enum { CT_MOVE = 0, CT_TILE = 1, CT_SCAN_DONE = 2, CT_RES_DONE = 3, CT_WORDS = 16 };
+enum { CT_MOVE = 0, CT_SCAN_DONE = 2, CT_RES_DONE = 3, CT_WORDS = 16 };
 
 struct ShardWs {
     unsigned* ctrl;      // [CT_WORDS]
     double* maxpart;     // [SMC_MAXPART]
     double* qpart;       // [n_tiles]
-    uint64_t* status;    // [2][n_tiles]
-    int64_t* cum;        // [n_max]   local inclusive cumsum of the fixed-point weights
+    int64_t* tile_off;   // [n_tiles + 1] tile totals, then (last CTA of the scan) their exclusive prefix; [n_tiles] = W
+    int64_t* cum;        // [n_max]   inclusive cumsum of the fixed-point weights WITHIN each tile
     char* extra;         // multinomial: all log-weights [M] + the single-GPU resampler's scratch
     size_t extra_bytes;
     int64_t n_tiles;
@@ -642,7 +646,7 @@ static size_t shard_ws_layout(void* ws, size_t ws_bytes, int64_t M, int world, S
     w.ctrl = ar.take<unsigned>(CT_WORDS);
     w.maxpart = ar.take<double>(SMC_MAXPART);
     w.qpart = ar.take<double>(n_tiles);
-    w.status = ar.take<uint64_t>(2 * n_tiles);
+    w.tile_off = ar.take<int64_t>(n_tiles + 1);
     w.cum = ar.take<int64_t>(n_max);
     w.extra = ar.take<char>(0);
     w.extra_bytes = ws_bytes > ar.off ? ws_bytes - ar.off : 0;
@@ -659,8 +663,7 @@ struct ScanArgs {
     uint64_t* mail_tab[BK_SMC_MAX_WORLD];
     uint64_t epoch;
     int64_t* cum;
-    uint64_t* status;       // this step's tile status words (zero on entry)
-    uint64_t* status_next;  // next step's (zeroed here)
+    int64_t* tile_off;
     double* qpart;
     unsigned* ctrl;
     int64_t n_tiles;
@@ -671,18 +674,17 @@ __device__ __forceinline__ int64_t fixed_weight(double lw, double gmax, int s) {
     return e == e ? __double2ll_rn(ldexp(e, s)) : 0;   // NaN log-weight: no mass
 }
 
-// One CTA per tile of 1024 particles, tiles handed out by a ticket (forward progress of the
-// look-back); single pass: tile aggregate -> decoupled look-back -> inclusive prefix.
+// One CTA per tile of 1024 particles: fixed-point weights, inclusive scan within the tile, tile total.
+// The last CTA to finish turns the tile totals into their exclusive prefix (one CTA, integer adds: a few
+// microseconds for thousands of tiles) and posts the local mass W and sum of squares Q to every rank.
 template <typename T>
 __global__ void __launch_bounds__(SC_THREADS) k_smc_scan(ScanArgs a) {
     __shared__ double gmax_s;
-    __shared__ unsigned tile_s;
     __shared__ int64_t wsum[SC_THREADS / 32];
-    __shared__ int64_t prefix_s;
     __shared__ double qred[33];
     __shared__ bool last_s;
+    __shared__ int64_t carry_s;
     uint64_t* mine = a.mail_tab[a.sh.rank];
-    if (threadIdx.x == 0) tile_s = atomicAdd(a.ctrl + CT_TILE, 1u);
     if (threadIdx.x < 32) {   // global max of the log-weights from the G max messages
         double v = -INFINITY;
         if ((int)threadIdx.x < a.sh.world) {
@@ -695,7 +697,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_smc_scan(ScanArgs a) {
     }
     __syncthreads();
     const double gmax = gmax_s;
-    const int64_t tile = tile_s;
+    const int64_t tile = blockIdx.x;
     const T* lw = (const T*)a.logw;
     const int64_t base = tile * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;
     int64_t v[SC_ITEMS], run = 0;
@@ -726,62 +728,64 @@ __global__ void __launch_bounds__(SC_THREADS) k_smc_scan(ScanArgs a) {
         if (i < wid) woff += wsum[i];
         agg += wsum[i];
     }
-    if (threadIdx.x == 0) {
-        double qs = 0.0;
-        for (int i = 0; i < SC_THREADS / 32; ++i) qs += qred[i];   // fixed order
-        a.qpart[tile] = qs;
-        a.status_next[tile] = 0;                                    // next step's word of this tile
-        // publish the aggregate, then look back for the exclusive prefix
-        int64_t excl = 0;
-        if (tile == 0) {
-            st_relaxed_gpu(a.status + tile, ST_INC | (uint64_t)agg);
-        } else {
-            st_relaxed_gpu(a.status + tile, ST_AGG | (uint64_t)agg);
-            for (int64_t p = tile - 1; p >= 0; --p) {
-                uint64_t w;
-                while (((w = ld_relaxed_gpu(a.status + p)) >> 62) == 0) __nanosleep(20);
-                excl += (int64_t)(w & ST_MASK);
-                if (w >> 62 == 2) break;
-            }
-            st_relaxed_gpu(a.status + tile, ST_INC | (uint64_t)(excl + agg));
-        }
-        prefix_s = excl;
-    }
-    __syncthreads();
-    const int64_t excl = prefix_s + woff + inc - run;
+    const int64_t excl = woff + inc - run;
 #pragma unroll
     for (int i = 0; i < SC_ITEMS; ++i) {
         const int64_t j = base + i;
         if (j < a.n) a.cum[j] = excl + v[i];
     }
-    // last CTA done: local mass W (inclusive prefix of the last tile) and sum of squares Q (fixed order)
-    // go to every rank's mailbox
-    __syncthreads();
     if (threadIdx.x == 0) {
+        double qs = 0.0;
+        for (int i = 0; i < SC_THREADS / 32; ++i) qs += qred[i];   // fixed order
+        a.qpart[tile] = qs;
+        a.tile_off[tile] = agg;
         __threadfence();
         last_s = atomicInc(a.ctrl + CT_SCAN_DONE, gridDim.x - 1) == gridDim.x - 1;
     }
     __syncthreads();
-    if (last_s) {
-        __threadfence();
-        double qs = 0.0;
-        for (int64_t i = threadIdx.x; i < a.n_tiles; i += SC_THREADS) qs += ld_relaxed_gpu_f64(a.qpart + i);
-        qs = warp_sum(qs);
-        __syncthreads();
-        if (lane == 0) qred[wid] = qs;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double t = 0.0;
-            for (int i = 0; i < SC_THREADS / 32; ++i) t += qred[i];
-            qred[32] = t;
-            a.ctrl[CT_TILE] = 0;   // every CTA has drawn its ticket
+    if (!last_s) return;
+    __threadfence();
+    // exclusive prefix of the tile totals, SC_THREADS tiles per round
+    if (threadIdx.x == 0) carry_s = 0;
+    double qs = 0.0;
+    __syncthreads();
+    for (int64_t t0 = 0; t0 < a.n_tiles; t0 += SC_THREADS) {
+        const int64_t t = t0 + threadIdx.x;
+        const int64_t x = t < a.n_tiles ? (int64_t)ld_relaxed_gpu((const uint64_t*)a.tile_off + t) : 0;
+        if (t < a.n_tiles) qs += ld_relaxed_gpu_f64(a.qpart + t);
+        int64_t in2 = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t y = __shfl_up_sync(0xffffffffu, in2, o);
+            if (lane >= o) in2 += y;
         }
+        if (lane == 31) wsum[wid] = in2;
         __syncthreads();
-        const uint64_t W = ld_relaxed_gpu(a.status + (a.n_tiles - 1)) & ST_MASK;
-        if ((int)threadIdx.x < a.sh.world)
-            mail_post3(a.mail_tab[threadIdx.x] + MB_MASS + ((a.epoch & 1) * BK_SMC_MAX_WORLD + a.sh.rank) * 4, W,
-                       (uint64_t)__double_as_longlong(qred[32]), (uint64_t)a.n, a.epoch);
+        int64_t wo = 0, tot = 0;
+#pragma unroll
+        for (int i = 0; i < SC_THREADS / 32; ++i) {
+            if (i < wid) wo += wsum[i];
+            tot += wsum[i];
+        }
+        const int64_t carry = carry_s;
+        if (t < a.n_tiles) a.tile_off[t] = carry + wo + in2 - x;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + tot;
+        __syncthreads();
     }
+    qs = warp_sum(qs);
+    if (lane == 0) qred[wid] = qs;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < SC_THREADS / 32; ++i) t += qred[i];
+        qred[32] = t;
+        a.tile_off[a.n_tiles] = carry_s;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < a.sh.world)
+        mail_post3(a.mail_tab[threadIdx.x] + MB_MASS + ((a.epoch & 1) * BK_SMC_MAX_WORLD + a.sh.rank) * 4, (uint64_t)carry_s,
+                   (uint64_t)__double_as_longlong(qred[32]), (uint64_t)a.n, a.epoch);
 }
 
 struct ResolveArgs {
@@ -789,8 +793,9 @@ struct ResolveArgs {
     uint64_t* mail_tab[BK_SMC_MAX_WORLD];
     int64_t* idx_tab[BK_SMC_MAX_WORLD];
     uint64_t epoch;
-    const int64_t* cum;     // local inclusive cumsum [n]
-    int64_t n;
+    const int64_t* cum;     // inclusive cumsum within each tile [n]
+    const int64_t* tile_off;  // exclusive prefix of the tile totals [n_tiles]
+    int64_t n, n_tiles;
     int shift_bits;
     const void* u0_in;      // injected u0 (dtype) or NULL
     bk_rng rng;
@@ -800,12 +805,14 @@ struct ResolveArgs {
     unsigned* ctrl;
 };
 
-// threshold of systematic point k in fixed-point CDF units: floor(((k + u0) / M) * W), clamped below W
-__device__ __forceinline__ int64_t sys_threshold(int64_t k, double u0, double Md, double Wd, int64_t W) {
-    const double t = __dmul_rn(__ddiv_rn(__dadd_rn((double)k, u0), Md), Wd);
-    int64_t ti = (int64_t)floor(t);
+// threshold of systematic point k in fixed-point CDF units: floor((k + u0) * (W / M)), clamped below W
+// (fp64 operations in this order; `rate` = (double)W / (double)M is formed once)
+__device__ __forceinline__ int64_t sys_threshold(int64_t k, double u0, double rate, int64_t W) {
+    const int64_t ti = (int64_t)floor(__dmul_rn(__dadd_rn((double)k, u0), rate));
     return ti < W ? ti : W - 1;
 }
+
+constexpr int RS_SMEM_TILES = 4096;   // tile offsets cached in shared memory (32 KB): 4 M particles per rank
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_smc_resolve(ResolveArgs a) {
@@ -815,6 +822,7 @@ __global__ void __launch_bounds__(256) k_smc_resolve(ResolveArgs a) {
     __shared__ double u0_s;
     __shared__ int resample_s;
     __shared__ bool last_s;
+    __shared__ int64_t toff_s[RS_SMEM_TILES];
     uint64_t* mine = a.mail_tab[a.sh.rank];
     if ((int)threadIdx.x < a.sh.world) {
         const uint64_t* slot = mine + MB_MASS + ((a.epoch & 1) * BK_SMC_MAX_WORLD + threadIdx.x) * 4;
@@ -822,6 +830,9 @@ __global__ void __launch_bounds__(256) k_smc_resolve(ResolveArgs a) {
         Ws[threadIdx.x] = (int64_t)ld_relaxed_sys(slot);
         Qs[threadIdx.x] = __longlong_as_double((long long)ld_relaxed_sys(slot + 1));
     }
+    const bool toff_in_smem = a.n_tiles <= RS_SMEM_TILES;
+    if (toff_in_smem)
+        for (int64_t i = threadIdx.x; i < a.n_tiles; i += blockDim.x) toff_s[i] = a.tile_off[i];
     __syncthreads();
     if (threadIdx.x == 0) {
         int64_t off = 0, tot = 0;
@@ -833,21 +844,28 @@ __global__ void __launch_bounds__(256) k_smc_resolve(ResolveArgs a) {
         }
         const double u0 = a.u0_in ? (double)((const T*)a.u0_in)[0]
                                   : (double)philox_uniform<T>(a.rng.seed, 0, 0u, (uint32_t)a.rng.draw_offset, TAG_RESAMPLE);
-        const double Wd = (double)tot, Md = (double)a.sh.M;
+        const double Wd = (double)tot, rate = Wd / (double)a.sh.M;
         int resample = 1;
         if (a.ess_threshold > 0) resample = (Wd * Wd / q < a.ess_threshold) ? 1 : 0;
         if (tot <= 0) { resample = 0; st_relaxed_sys(mine + MB_ERR, 2ull); }   // every weight vanished: keep the particles
-        // first point whose threshold reaches `target` (thresholds are monotone in k)
+        // first point whose threshold reaches `target` (thresholds are monotone in k): estimate, then fix up
         auto first_at = [&](int64_t target) {
+            if (target <= 0) return (int64_t)0;
             int64_t lo = 0, hi = a.sh.M;
+            const double guess = (double)target / rate - u0;
+            int64_t g = (int64_t)guess;
+            if (g > 4 && g < a.sh.M - 4) {        // narrow the bracket around the estimate when it is consistent
+                if (sys_threshold(g - 4, u0, rate, tot) < target) lo = g - 4;
+                if (sys_threshold(g + 4, u0, rate, tot) >= target) hi = g + 4;
+            }
             while (lo < hi) {
                 const int64_t mid = (lo + hi) >> 1;
-                if (sys_threshold(mid, u0, Md, Wd, tot) < target) lo = mid + 1; else hi = mid;
+                if (sys_threshold(mid, u0, rate, tot) < target) lo = mid + 1; else hi = mid;
             }
             return lo;
         };
         k_lo_s = resample ? first_at(off) : 0;
-        k_hi_s = resample ? first_at(off + Ws[a.sh.rank]) : 0;
+        k_hi_s = resample ? (a.sh.rank == a.sh.world - 1 ? a.sh.M : first_at(off + Ws[a.sh.rank])) : 0;
         off_s = off; tot_s = tot; u0_s = u0; resample_s = resample;
         if (blockIdx.x == 0 && a.stats_out) {
             double mx = -INFINITY;
@@ -864,18 +882,52 @@ __global__ void __launch_bounds__(256) k_smc_resolve(ResolveArgs a) {
     const int64_t lo_r = shard_lo(a.sh, a.sh.rank);
     if (resample_s) {
         const int64_t k_lo = k_lo_s, k_hi = k_hi_s, off = off_s, tot = tot_s;
-        const double u0 = u0_s, Wd = (double)tot, Md = (double)a.sh.M;
-        for (int64_t k = k_lo + gtid; k < k_hi; k += gstride) {
-            const int64_t t = sys_threshold(k, u0, Md, Wd, tot) - off;   // in [0, W_r)
-            int64_t lo = 0, hi = a.n;                                    // first j with cum[j] > t
+        const double u0 = u0_s, rate = (double)tot / (double)a.sh.M;
+        const int64_t* toff = toff_in_smem ? toff_s : a.tile_off;
+        // a thread resolves RS_POINTS consecutive points: one two-level search (tile offsets, then inside the
+        // tile) for the first, a short forward walk for the others (consecutive points sit ~1 particle apart)
+        for (int64_t k0 = k_lo + gtid * RS_POINTS; k0 < k_hi; k0 += gstride * RS_POINTS) {
+            int64_t t = sys_threshold(k0, u0, rate, tot) - off;          // in [0, W_r)
+            int64_t tl = 0, th = a.n_tiles;                              // last tile with toff <= t
+            while (th - tl > 1) {
+                const int64_t mid = (tl + th) >> 1;
+                if (toff[mid] <= t) tl = mid; else th = mid;
+            }
+            int64_t tile = tl, tbase = toff[tile];
+            int64_t jend = (tile + 1) * SC_TILE < a.n ? (tile + 1) * SC_TILE : a.n;
+            int64_t lo = tile * SC_TILE, hi = jend;                      // first j in the tile with cum[j] > t - tbase
             while (lo < hi) {
                 const int64_t mid = (lo + hi) >> 1;
-                if (a.cum[mid] <= t) lo = mid + 1; else hi = mid;
+                if (a.cum[mid] <= t - tbase) lo = mid + 1; else hi = mid;
             }
-            if (lo >= a.n) lo = a.n - 1;
-            int owner; int64_t loc;
-            shard_locate(a.sh, k, owner, loc);
-            a.idx_tab[owner][loc] = lo_r + lo;     // peer store: the slot's owner reads it in its next move
+            int64_t j = lo;
+#pragma unroll 1
+            for (int p = 0; p < RS_POINTS; ++p) {
+                const int64_t k = k0 + p;
+                if (k >= k_hi) break;
+                if (p > 0) {
+                    t = sys_threshold(k, u0, rate, tot) - off;
+                    // advance to the first particle whose global inclusive cumsum exceeds t
+                    while (true) {
+                        if (j >= jend) {                                   // tile exhausted: next tile with mass
+                            if (jend >= a.n) { j = a.n - 1; break; }
+                            ++tile; tbase = toff[tile];
+                            jend = (tile + 1) * SC_TILE < a.n ? (tile + 1) * SC_TILE : a.n;
+                            j = tile * SC_TILE;
+                            continue;
+                        }
+                        if (tbase + a.cum[j] > t) break;
+                        ++j;
+                    }
+                } else if (j >= jend) {
+                    // t falls on a tile whose remaining particles carry no mass beyond it (cannot happen when
+                    // toff[tile + 1] > t, which the tile search guarantees) -- clamp defensively
+                    j = jend - 1;
+                }
+                int owner; int64_t loc;
+                shard_locate(a.sh, k, owner, loc);
+                a.idx_tab[owner][loc] = lo_r + j;     // peer store: the slot's owner reads it in its next move
+            }
         }
         if (a.ess_threshold > 0)                   // equal weights after an adaptive step resampled
             for (int64_t i = gtid; i < a.n; i += gstride) ((T*)a.logw)[i] = T(0);
@@ -1244,8 +1296,7 @@ int bk_smc_shard_resample(const bk_smc_shard* sh, int32_t dtype, int32_t mode, c
             for (int q = 0; q < g.world; ++q) a.mail_tab[q] = (uint64_t*)sh->mailbox[q];
             a.epoch = sh->epoch;
             a.cum = w.cum;
-            a.status = w.status + (sh->epoch & 1) * w.n_tiles;
-            a.status_next = w.status + ((sh->epoch & 1) ^ 1) * w.n_tiles;
+            a.tile_off = w.tile_off;
             a.qpart = w.qpart;
             a.ctrl = w.ctrl;
             a.n_tiles = (n + SC_TILE - 1) / SC_TILE;
@@ -1263,7 +1314,9 @@ int bk_smc_shard_resample(const bk_smc_shard* sh, int32_t dtype, int32_t mode, c
             }
             a.epoch = sh->epoch;
             a.cum = w.cum;
+            a.tile_off = w.tile_off;
             a.n = n;
+            a.n_tiles = (n + SC_TILE - 1) / SC_TILE;
             a.shift_bits = s_bits;
             a.u0_in = uniforms;
             a.rng = r;
@@ -1272,8 +1325,8 @@ int bk_smc_shard_resample(const bk_smc_shard* sh, int32_t dtype, int32_t mode, c
             a.stats_out = stats_out;
             a.ctrl = w.ctrl;
             // the expected number of points per rank is n; a rank holding most of the mass gets more (grid-stride)
-            int64_t blocks = (n + 255) / 256;
-            const int64_t cap = (int64_t)device_sms() * 8;
+            int64_t blocks = (n + 256 * RS_POINTS - 1) / (256 * RS_POINTS);
+            const int64_t cap = (int64_t)device_sms() * 4;
             if (blocks > cap) blocks = cap;
             if (blocks < 1) blocks = 1;
             if (dtype == BK_F64) k_smc_resolve<double><<<(unsigned)blocks, 256, 0, st>>>(a);

@@ -257,7 +257,7 @@ BK_API int bk_gather_rows(const void* src, const int64_t* idx, int64_t M, int64_
  *   particle rows (next move kernel)          row idx[m] read from its owner's array   D * s per row
  * SYSTEMATIC resampling is defined in exact integer arithmetic so that the indices do not depend on
  * G:  w_i = rint(exp(logw_i - max) * 2^s),  s = 61 - ceil(log2 M);  C = cumsum(w) (int64, exact);
- * point k has threshold t_k = floor(((k + u0) / M) * W) (fp64 ops in this order, W = sum w, clamped to
+ * point k has threshold t_k = floor((k + u0) * (W / M)) (fp64 ops in this order, W = sum w, clamped to
  * W - 1) and selects the first particle with C > t_k.  Rank r resolves exactly the points whose
  * threshold falls into its own interval [O_r, O_r + W_r).  MULTINOMIAL (the reference's
  * np.random.choice, smc.py:64-75) keeps its fp64 CDF: every rank reads all log-weights from its

@@ -301,14 +301,14 @@ def systematic_weights(logw):
 def systematic_indices(logw, u0):
     """Systematic resampling with a log-sum-exp normaliser (north_star item 2;
     NOT in the reference -- parity unpinned, this restatement is the oracle).
-    Point k has threshold t_k = floor(((k + u0) / M) * W) in fixed-point CDF units (W = sum w, fp64
-    operations in exactly this order, clamped to W - 1) and selects the first particle whose
+    Point k has threshold t_k = floor((k + u0) * (W / M)) in fixed-point CDF units (W = sum w, fp64
+    operations in exactly this order, the rate W / M formed once, clamped to W - 1) and selects the first particle whose
     inclusive integer cumsum exceeds t_k."""
     w, _ = systematic_weights(logw)
     M = w.shape[0]
     cum = np.cumsum(w)
     W = int(cum[-1])
-    t = np.floor(((np.arange(M) + u0) / M) * float(W)).astype(np.int64)
+    t = np.floor((np.arange(M) + u0) * (float(W) / M)).astype(np.int64)
     t = np.minimum(t, W - 1)
     idx = np.searchsorted(cum, t, side="right")
     return np.minimum(idx, M - 1).astype(np.int64), cum
