@@ -12,6 +12,7 @@
 // recomputation: a deterministic plugin returns identical values, so the
 // kernel recomputes log p and its gradient from the position.
 #include <stdlib.h>
+#include "drghmc_generic.h"
 #include "model.h"
 #include "sep_common.cuh"
 
@@ -294,9 +295,18 @@ using namespace bk;
 
 extern "C" {
 
+// the fused register-resident kernel serves iso / diagonal Gaussian plugins up to 256 dims; everything else
+// (dense precision, logistic regression, binomial, D > 256) runs on the lockstep engine of drghmc_generic.cu
+static bool drghmc_fused(const Model& m) {
+    const char* e = getenv("BK_FORCE_GENERIC");   // test hook: both engines must produce the same chains
+    const bool force = e && e[0] == '1';
+    return !force && m.separable() && m.d.dims <= 256;
+}
+
 size_t bk_drghmc_workspace_bytes(uint64_t handle, int64_t C, int32_t max_proposals) {
-    (void)handle; (void)C; (void)max_proposals;
-    return 0;
+    const Model* m = get_model(handle);
+    if (!m || drghmc_fused(*m)) return 0;
+    return drghmc_generic_ws_bytes(*m, C, max_proposals);
 }
 
 int bk_drghmc_sample(uint64_t handle, void* theta, void* rho, int64_t C, int32_t max_proposals,
@@ -304,7 +314,6 @@ int bk_drghmc_sample(uint64_t handle, void* theta, void* rho, int64_t C, int32_t
                      int32_t prob_retry, const void* metric, int64_t n_draws, const bk_rng* rng,
                      const bk_draw_out* out, int32_t* n_uniform_used_out, void* ws, size_t ws_bytes,
                      void* stream) {
-    (void)ws; (void)ws_bytes;
     const Model* m = get_model(handle);
     if (!m) return BK_E_HANDLE;
     BK_CHECK_ARG(theta && rho && C >= 0 && n_draws >= 0, "bk_drghmc_sample: bad theta/rho/C/n_draws");
@@ -326,12 +335,11 @@ int bk_drghmc_sample(uint64_t handle, void* theta, void* rho, int64_t C, int32_t
         set_error("bk_drghmc_sample supports max_proposals <= %d (got %d)", DR_KMAX, max_proposals);
         return BK_E_UNSUPPORTED;
     }
-    if (!m->separable()) {
-        set_error("bk_drghmc_sample: only iso/diagonal Gaussian plugins have a fused DrGHMC kernel");
-        return BK_E_UNSUPPORTED;
-    }
     bk_draw_out o = out ? *out : bk_draw_out{nullptr, nullptr, nullptr};
     if (C == 0 || n_draws == 0) return BK_OK;
+    if (!drghmc_fused(*m))
+        return drghmc_generic(*m, theta, rho, C, max_proposals, step_sizes_host, step_counts_host, damping, prob_retry,
+                              metric, n_draws, rng, o, n_uniform_used_out, ws, ws_bytes, (cudaStream_t)stream);
     if (m->d.dtype == BK_F64)
         return drghmc_t<double>(*m, theta, rho, C, max_proposals, step_sizes_host, step_counts_host,
                                 damping, prob_retry, metric, n_draws, rng, o, n_uniform_used_out,

@@ -118,8 +118,8 @@ struct BinomView {
 // resample index and the particle row of the NEXT visit are requested before the current particle is
 // processed (two dependent global loads deep), the accept uniform is drawn by the group's first lane only.
 // MOVE selects the Markov kernel applied at temperature t0 = time(n-1) (smc.py:54-57).
-template <typename T, int G, int J, template <typename, int, int> class View, int MOVE>
-__global__ void __launch_bounds__(128, (J >= 4 && sizeof(T) == 4) ? 3 : (J == 2 && G == 8) ? 5 : 1) k_smc_move_weight(SmcArgs<T> a) {
+template <typename T, int G, int J, template <typename, int, int> class View, int MOVE, int OCC = 0>
+__global__ void __launch_bounds__(128, OCC ? OCC : (J >= 4 && sizeof(T) == 4) ? 3 : (J == 2 && G == 8) ? 5 : 1) k_smc_move_weight(SmcArgs<T> a) {
     using A = Ar<T>;
     constexpr int NE = 4 * J;
     const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / G;
@@ -306,7 +306,7 @@ static int device_sms() {
     return sms;
 }
 
-template <typename T, int G, int J, template <typename, int, int> class View, int MOVE>
+template <typename T, int G, int J, template <typename, int, int> class View, int MOVE, int OCC = 0>
 static int launch_smc3(const SmcArgs<T>& a, cudaStream_t st) {
     const int64_t per_block = 128 / G;
     const int64_t need = (a.M + per_block - 1) / per_block;
@@ -315,7 +315,7 @@ static int launch_smc3(const SmcArgs<T>& a, cudaStream_t st) {
     static int64_t cap = 0;
     if (!cap) {
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_smc_move_weight<T, G, J, View, MOVE>, 128, 0) != cudaSuccess || nb < 1) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_smc_move_weight<T, G, J, View, MOVE, OCC>, 128, 0) != cudaSuccess || nb < 1) {
             cudaGetLastError();
             nb = 1;
         }
@@ -323,7 +323,7 @@ static int launch_smc3(const SmcArgs<T>& a, cudaStream_t st) {
     }
     int64_t blocks = need < cap ? need : cap;
     if (blocks > SMC_MAXPART) blocks = SMC_MAXPART;
-    k_smc_move_weight<T, G, J, View, MOVE><<<(unsigned)blocks, 128, 0, st>>>(a);
+    k_smc_move_weight<T, G, J, View, MOVE, OCC><<<(unsigned)blocks, 128, 0, st>>>(a);
     BK_LAUNCH_CHECK();
     return BK_OK;
 }
@@ -372,6 +372,10 @@ static int smc_dispatch(const Model& m, SmcArgs<T>& a, const bk_smc_kernel& kn, 
         static int layout = -1;   // BK_SMC_LAYOUT (diagnostic): 2 = 4 x 16 (default), 1 = 8 x 8, 0 = 16 x 4
         if (layout < 0) { const char* e = getenv("BK_SMC_LAYOUT"); layout = e ? atoi(e) : 2; }
         if (wide && D > 32 && D <= 64 && kn.kind == BK_SMC_KERNEL_RW) {
+            static int occ = -1;
+            if (occ < 0) { const char* e = getenv("BK_SMC_OCC"); occ = e ? atoi(e) : 0; }
+            if (layout == 2 && occ == 2) return launch_smc3<T, 4, 4, GplView, BK_SMC_KERNEL_RW, 2>(a, st);
+            if (layout == 2 && occ == 4) return launch_smc3<T, 4, 4, GplView, BK_SMC_KERNEL_RW, 4>(a, st);
             if (layout == 2) return launch_smc3<T, 4, 4, GplView, BK_SMC_KERNEL_RW>(a, st);
             if (layout == 1) return launch_smc3<T, 8, 2, GplView, BK_SMC_KERNEL_RW>(a, st);
         }

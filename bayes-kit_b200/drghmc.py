@@ -46,6 +46,8 @@ class DrGhmcDiag(ChainSampler):
             m = to_dev(metric_diag, self.dtype, self.device).reshape(-1)
             if m.numel() == 1 and self._dim > 1:
                 m = m.expand(self._dim).contiguous()
+            if m.numel() != self._dim:
+                raise ValueError(f"metric_diag must have {self._dim} entries")
             self._metric = m
         # rho0 ~ N(0, I) (drghmc.py:77)
         g = torch.Generator(device=self.device)

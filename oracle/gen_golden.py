@@ -22,8 +22,8 @@ import numpy as np
 
 from . import diagnostics as od
 from . import samplers as osm
-from .models import (DensePrecGauss, DiagGauss, GaussPriorLik, HierLogReg, IsoGauss,
-                     model_spec)
+from .models import (Binomial, DensePrecGauss, DiagGauss, GaussPriorLik, HierLogReg, IsoGauss,
+                     Tempered, model_spec)
 from .record import LegacyRecorder, RecordingGenerator, load_reference, record_chain
 
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
@@ -193,6 +193,103 @@ def gen_smc(bk, tag, model, M, T, scale):
                         thetas_final=np.asarray(smc.thetas), scale=scale, T=T)
 
 
+class _LegacyRng:
+    """`_rng` stand-in for a reference sampler used as an SMC kernel: draws from the process-global legacy
+    stream like smc.py's own kernel does (smc.py:81,85), through the entry points LegacyRecorder patches."""
+
+    def normal(self, loc=0.0, scale=1.0, size=None):
+        return np.random.normal(loc=loc, scale=scale, size=size)
+
+    def uniform(self):
+        return np.random.uniform()
+
+
+def gen_smc_kernel(bk, tag, model, M, T, kernel):
+    """TemperedLikelihoodSMC (unmodified) with an MCMC kernel built from the reference's OWN MALA / HMCDiag
+    classes on the tempered model -- the plug-in the TODO at smc.py:78 asks for.  kernel = ("mala", eps) or
+    ("hmc", eps, L).  The kernel closure counts its calls to know the temperature (smc.py:54-57 hands it only
+    theta and the log density)."""
+    D = model.dims()
+    init_rng = np.random.default_rng(13)
+    thetas0 = init_rng.normal(size=(M, D))
+    calls = [0]
+
+    def kern(theta, lpminus1):
+        n = 1 + calls[0] // M
+        calls[0] += 1
+        tm = Tempered(model, (n - 1) / T)
+        assert abs(tm.log_density(theta) - lpminus1(theta)) <= 1e-12 * max(1.0, abs(lpminus1(theta)))
+        if kernel[0] == "mala":
+            s = bk.MALA(tm, kernel[1], init=np.array(theta, copy=True))
+        else:
+            s = bk.HMCDiag(tm, kernel[1], kernel[2], init=np.array(theta, copy=True))
+        s._rng = _LegacyRng()
+        return np.array(s.sample()[0], copy=True)
+
+    np.random.seed(77)
+    with LegacyRecorder() as rec:
+        smc = bk.TemperedLikelihoodSMC(model, M, T, lambda m: thetas0[m].copy(), kern)
+        smc.run()
+    normals = np.stack(rec.normals).reshape(T, M, D)
+    acc_u = np.array(rec.uniforms).reshape(T, M)
+    res_u = np.stack(rec.res_uniforms)
+    idx = np.stack(rec.indices)
+    o_th, o_idx = osm.smc_tempered(model, thetas0, normals, acc_u, res_u, 0.0, T, kernel=kernel)
+    print(tag)
+    assert np.array_equal(o_idx, idx), "resample indices differ"
+    _check("final particles", o_th, np.asarray(smc.thetas), 1e-13)
+    np.savez_compressed(os.path.join(OUT, tag + ".npz"), **model_spec(model), thetas0=thetas0, normals=normals,
+                        acc_uniforms=acc_u, res_uniforms=res_u, indices=idx, thetas_final=np.asarray(smc.thetas),
+                        scale=float(kernel[1]), T=T, kernel_kind=kernel[0],
+                        kernel_steps=int(kernel[2]) if len(kernel) > 2 else 0)
+
+
+def check_binomial_against_upstream():
+    """oracle.models.Binomial == the reference's test/models/binomial.py densities (scipy), 1e-12."""
+    sys.path.insert(0, "/root/reference")
+    try:
+        from test.models.binomial import Binomial as UpBinomial
+    finally:
+        sys.path.remove("/root/reference")
+    up, mine = UpBinomial(alpha=2, beta=3, x=5, N=15), Binomial(2, 3, 5, 15)
+    for th in np.linspace(-6, 6, 25):
+        v = np.array([th])
+        assert abs(up.log_prior(v) - mine.log_prior(v)) < 1e-12 * max(1, abs(up.log_prior(v)))
+        assert abs(up.log_likelihood(v) - mine.log_likelihood(v)) < 1e-12 * max(1, abs(up.log_likelihood(v)))
+        lp, g = mine.log_density_gradient(v)
+        fd = (mine.log_density(v + 1e-6) - mine.log_density(v - 1e-6)) / 2e-6
+        assert abs(g[0] - fd) < 1e-6
+    print("oracle Binomial == upstream test model (log_prior, log_likelihood), analytic gradient == FD")
+
+
+def gen_round2(bk):
+    """Fixtures added in round 2: DrGhmcDiag on the non-separable plugins (lockstep engine), the reference's
+    own beta-binomial test target under SMC / DrGHMC / HMC, and MALA / HMC kernels inside the SMC."""
+    rng = np.random.default_rng(2)
+    check_binomial_against_upstream()
+    P64 = DensePrecGauss.c2_precision(64)
+    gen_drghmc(bk, "drghmc_dense_d64", DensePrecGauss(P64), n=14, C=4, K=3, sizes=[0.45, 0.2, 0.1], counts=[3, 5, 8],
+               damping=0.4, prob_retry=True)
+    gen_drghmc(bk, "drghmc_dense_d64_retry0", DensePrecGauss(P64, mu=rng.normal(size=64)), n=10, C=3, K=2,
+               sizes=[0.5, 0.2], counts=[4, 6], damping=1.0, prob_retry=False)
+    gen_drghmc(bk, "drghmc_dense_d1000", DensePrecGauss(DensePrecGauss.c2_precision(1000)), n=3, C=2, K=2,
+               sizes=[0.12, 0.05], counts=[4, 8], damping=0.5, prob_retry=True)
+    X, y = HierLogReg.c3_data(400, 6, seed=0)
+    gen_drghmc(bk, "drghmc_hlr_n400_d6", HierLogReg(X, y), n=12, C=3, K=2, sizes=[0.12, 0.05], counts=[3, 6],
+               damping=0.3, prob_retry=True)
+    bn = Binomial(2, 3, 5, 15)
+    gen_drghmc(bk, "drghmc_binom", bn, n=40, C=4, K=3, sizes=[0.9, 0.4, 0.1], counts=[3, 3, 3], damping=0.2,
+               prob_retry=True)       # test_drghmc.py:151-176's target (larger first step: exercises the retries)
+    gen_hmc(bk, "hmc_binom", bn, n=30, C=4, eps=0.2, L=4)               # test_hmc.py:68-86's target
+    gen_mala(bk, "mala_binom", bn, n=30, C=4, eps=0.3)                  # test_mala.py:25-41's target
+    gen_smc(bk, "smc_binom", bn, M=75, T=15, scale=0.5)                 # test_tempered_smc.py:8-30, literally
+    mu = rng.normal(size=5)
+    gpl = GaussPriorLik(np.zeros(5), np.ones(5), mu, 4.0 * np.ones(5))
+    gen_smc_kernel(bk, "smc_gauss_d5_mala", gpl, M=60, T=5, kernel=("mala", 0.05))
+    gen_smc_kernel(bk, "smc_gauss_d5_hmc", gpl, M=60, T=5, kernel=("hmc", 0.2, 3))
+    gen_smc_kernel(bk, "smc_binom_hmc", bn, M=50, T=6, kernel=("hmc", 0.3, 2))
+
+
 def gen_diagnostics(bk):
     from bayes_kit.autocorr import autocorr as r_autocorr
     from bayes_kit.rhat import rhat as r_rhat, split_rhat as r_split_rhat
@@ -245,6 +342,9 @@ def main():
     bk = load_reference()
     np.seterr(all="ignore")
     rng = np.random.default_rng(0)
+    if "--round2" in sys.argv:          # only the fixtures added in round 2 (the others are unchanged)
+        gen_round2(bk)
+        return 0
 
     gen_hmc(bk, "hmc_iso_d100", IsoGauss(100), n=25, C=4, eps=0.1, L=10)
     gen_hmc(bk, "hmc_iso_d100_big_eps", IsoGauss(100), n=25, C=4, eps=0.8, L=7)
@@ -300,6 +400,7 @@ def main():
                    for e in np.eye(8)])
     _check("hier_logreg grad vs FD", g, fd, 1e-6)
     gen_hmc(bk, "hmc_hlr_n400_d6", hl, n=15, C=3, eps=0.05, L=6)
+    gen_round2(bk)
     print("all fixtures written to", os.path.normpath(OUT))
 
 

@@ -117,6 +117,81 @@ class GaussPriorLik:
         g = -(self.pl * (theta - self.mu)) - self.p0 * (theta - self.m0)
         return self.log_density(theta), g
 
+    def log_likelihood_gradient(self, theta):
+        return -(self.pl * (theta - self.mu))
+
+    def log_prior_gradient(self, theta):
+        return -(self.p0 * (theta - self.m0))
+
+
+class Binomial:
+    """Beta-binomial on the logit scale -- the reference's own test target
+    (``test/models/binomial.py:11-74``, used by test_tempered_smc.py:8-30, test_hmc.py:69,
+    test_mala.py:26, test_drghmc.py:152) restated with elementary functions and an ANALYTIC
+    gradient (the upstream test model differentiates numerically, binomial.py:59-65):
+        p = inv_logit(theta);  log_likelihood = log C(N, x) + x log p + (N - x) log(1 - p)
+        log_prior = Beta(p; alpha, beta) + log p + log(1 - p)        (logit Jacobian, binomial.py:46-50)
+                  = alpha log p + beta log(1 - p) - log B(alpha, beta)
+    gen_golden.py checks both densities against the upstream class (scipy) to 1e-12."""
+
+    def __init__(self, alpha, beta, x, N):
+        import math
+        self.alpha, self.beta, self.x, self.N = float(alpha), float(beta), float(x), float(N)
+        self.lchoose = math.lgamma(N + 1) - math.lgamma(x + 1) - math.lgamma(N - x + 1)
+        self.lbeta = math.lgamma(alpha) + math.lgamma(beta) - math.lgamma(alpha + beta)
+
+    def dims(self) -> int:
+        return 1
+
+    @staticmethod
+    def _logs(th):
+        e = np.exp(-np.abs(th))
+        l = np.log1p(e)
+        lp1 = -l if th >= 0 else th - l              # log p     = -softplus(-theta)
+        l1m = -th - l if th >= 0 else -l             # log (1-p) = -softplus(theta)
+        p = 1.0 / (1.0 + e) if th >= 0 else e / (1.0 + e)
+        return lp1, l1m, p
+
+    def log_likelihood(self, theta):
+        lp1, l1m, _ = self._logs(float(theta[0]))
+        return (self.lchoose + self.x * lp1) + (self.N - self.x) * l1m
+
+    def log_prior(self, theta):
+        lp1, l1m, _ = self._logs(float(theta[0]))
+        return (self.alpha * lp1 + self.beta * l1m) - self.lbeta
+
+    def log_density(self, theta):
+        return self.log_likelihood(theta) + self.log_prior(theta)
+
+    def log_likelihood_gradient(self, theta):
+        _, _, p = self._logs(float(theta[0]))
+        return np.array([self.x - self.N * p])
+
+    def log_prior_gradient(self, theta):
+        _, _, p = self._logs(float(theta[0]))
+        return np.array([self.alpha - (self.alpha + self.beta) * p])
+
+    def log_density_gradient(self, theta):
+        return self.log_density(theta), self.log_likelihood_gradient(theta) + self.log_prior_gradient(theta)
+
+
+class Tempered:
+    """``lp_t(theta) = log_likelihood(theta) * t + log_prior(theta)`` (smc.py:47-51) as a GradModel,
+    gradient ``grad_ll * t + grad_prior``: what an MCMC kernel inside the SMC targets."""
+
+    def __init__(self, model, t):
+        self.model, self.t = model, float(t)
+
+    def dims(self) -> int:
+        return self.model.dims()
+
+    def log_density(self, theta):
+        return self.model.log_likelihood(theta) * self.t + self.model.log_prior(theta)
+
+    def log_density_gradient(self, theta):
+        g = self.model.log_likelihood_gradient(theta) * self.t + self.model.log_prior_gradient(theta)
+        return self.log_density(theta), g
+
 
 class HierLogReg:
     """Hierarchical logistic regression (BASELINE config c3; builder-defined,
@@ -186,6 +261,8 @@ def model_spec(model) -> dict:
                     model_mu=model.mu, model_pl=model.pl)
     if isinstance(model, HierLogReg):
         return dict(model_kind="hlr", model_X=model.X, model_y=model.y)
+    if isinstance(model, Binomial):
+        return dict(model_kind="binom", model_abxn=np.array([model.alpha, model.beta, model.x, model.N]))
     raise TypeError(type(model))
 
 
@@ -204,4 +281,7 @@ def build_model(z):
         return GaussPriorLik(z["model_m0"], z["model_p0"], z["model_mu"], z["model_pl"])
     if kind == "hlr":
         return HierLogReg(z["model_X"], z["model_y"])
+    if kind == "binom":
+        a, b, x, n = z["model_abxn"]
+        return Binomial(a, b, int(x), int(n))
     raise ValueError(kind)

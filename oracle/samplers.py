@@ -314,17 +314,41 @@ def systematic_indices(logw, u0):
     return np.minimum(idx, M - 1).astype(np.int64), cum
 
 
+def smc_move(model, theta, t0, z, u, kernel):
+    """One application of the SMC's Markov kernel at temperature t0 to one particle.
+    kernel = ("rw", scale): metropolis_kernel (smc.py:79-89);
+             ("mala", eps): one MALA.sample() on the tempered density (mala.py:40-66);
+             ("hmc", eps, L): one HMCDiag.sample(), identity metric (hmc.py:40-63) -- the MCMC-kernel
+             plug-ins of the TODO at smc.py:78, pinned by gen_golden.py against the reference's own MALA /
+             HMCDiag classes driven on the tempered model."""
+    from .models import Tempered
+    kind = kernel[0]
+    if kind == "rw":
+        lp = lambda th: model.log_likelihood(th) * t0 + model.log_prior(th)
+        star = theta + kernel[1] * z
+        return star if _log_u(u) < lp(star) - lp(theta) else theta
+    tm = Tempered(model, t0)
+    if kind == "mala":
+        d, _, _ = mala(tm, theta, z[None], np.array([u]), kernel[1])
+        return d[0]
+    if kind == "hmc":
+        d, _, _ = hmc_diag(tm, theta, z[None], np.array([u]), kernel[1], kernel[2])
+        return d[0]
+    raise ValueError(kind)
+
+
 def smc_tempered(model, thetas0, prop_normals, acc_uniforms, res_uniforms,
-                 scale, T, resample="multinomial"):
-    """Full run of TemperedLikelihoodSMC with the RW-Metropolis kernel.
+                 scale, T, resample="multinomial", kernel=None):
+    """Full run of TemperedLikelihoodSMC.
 
     ``run``/``transition`` (smc.py:39-60): for n = 1..T move every particle
-    once with ``metropolis_kernel(scale)`` (smc.py:79-89) targeting the
+    once with the kernel (default ``metropolis_kernel(scale)``, smc.py:79-89) targeting the
     PREVIOUS temperature, then reweight to ``time(n)`` and resample.
     prop_normals [T, M, D], acc_uniforms [T, M], res_uniforms [T, M]
     (systematic: only res_uniforms[:, 0] is used).
     Returns (thetas_final [M, D], idx [T, M]).
     """
+    kernel = ("rw", scale) if kernel is None else kernel
     thetas = np.array(thetas0, dtype=np.float64, copy=True)
     M = thetas.shape[0]
     all_idx = np.empty((T, M), dtype=np.int64)
@@ -335,9 +359,7 @@ def smc_tempered(model, thetas0, prop_normals, acc_uniforms, res_uniforms,
             return model.log_likelihood(th) * t0 + model.log_prior(th)
 
         for m in range(M):
-            star = thetas[m] + scale * prop_normals[n - 1, m]
-            if _log_u(acc_uniforms[n - 1, m]) < lpm1(star) - lpm1(thetas[m]):
-                thetas[m] = star
+            thetas[m] = smc_move(model, thetas[m], t0, prop_normals[n - 1, m], acc_uniforms[n - 1, m], kernel)
         if resample == "multinomial":
             w = smc_weights(model, thetas, n, T)
             idx, _ = multinomial_indices(w, res_uniforms[n - 1])

@@ -19,7 +19,20 @@ def device_model(bk, z, dtype=torch.float64):
         return bk.GaussPriorLik(z["model_m0"], z["model_p0"], z["model_mu"], z["model_pl"], dtype=dtype)
     if kind == "hlr":
         return bk.HierLogReg(z["model_X"], z["model_y"], dtype=dtype)
+    if kind == "binom":
+        a, b, x, n = z["model_abxn"]
+        return bk.Binomial(float(a), float(b), int(x), int(n), dtype=dtype)
     raise ValueError(kind)
+
+
+def smc_kernel(bk, z):
+    """The SMC move kernel a fixture was recorded with (default: metropolis_kernel(scale))."""
+    kind = str(z["kernel_kind"]) if "kernel_kind" in z.files else "rw"
+    if kind == "mala":
+        return bk.mala_kernel(float(z["scale"]))
+    if kind == "hmc":
+        return bk.hmc_kernel(float(z["scale"]), int(z["kernel_steps"]))
+    return bk.metropolis_kernel(float(z["scale"]))
 
 
 def np_(t):

@@ -65,10 +65,14 @@ def test_drghmc(name):
 @pytest.mark.parametrize("name", _names("smc_"))
 def test_smc(name):
     z = golden(name)
+    kernel = None
+    if "kernel_kind" in z.files:      # MALA / HMC kernels inside the SMC (recorded with the reference's own classes)
+        kind = str(z["kernel_kind"])
+        kernel = (kind, float(z["scale"])) if kind == "mala" else (kind, float(z["scale"]), int(z["kernel_steps"]))
     th, idx = osm.smc_tempered(build_model(z), z["thetas0"], z["normals"], z["acc_uniforms"],
-                               z["res_uniforms"], float(z["scale"]), int(z["T"]))
+                               z["res_uniforms"], float(z["scale"]), int(z["T"]), kernel=kernel)
     assert np.array_equal(idx, z["indices"])
-    assert np.array_equal(th, z["thetas_final"])
+    _close(th, z["thetas_final"])
 
 
 @pytest.mark.parametrize("tag", ["n37", "n1000", "n10000"])
