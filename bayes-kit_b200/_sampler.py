@@ -242,6 +242,89 @@ class ChainSampler:
         s_out.synchronize()
         return draw_h, logp_h
 
+    def sample_host_n(self, n: int, theta_host=None, out=None, chunk_chains=None):
+        """``n`` draws of every chain with HOST buffers -- what a caller of the reference ends up with after
+        ``[sampler.sample() for _ in range(n)]`` (host arrays, hmc.py:63): the chain state goes in ONCE
+        (``theta_host`` [C, D], optional), all n draws and log densities come back
+        (``out = (draws_host [n, C, D], logp_host [n, C])``, pinned; allocated when None).  Chains are cut into
+        chunks; chunk k's device->host copies, chunk k+1's kernels (n draws) and chunk k+2's host->device copy
+        run concurrently on three streams, with a ring of three device staging buffers.  Chunking cannot change
+        the result (Philox is keyed by the global chain id).  Returns (draws_host, logp_host), complete on
+        return; ``last_accept`` [n, C] stays on the device."""
+        if self._single:
+            raise ValueError("sample_host_n is the batched surface: construct with init [C, D] or chains=C")
+        n = int(n)
+        C_, D = self._C, self._dim
+        if out is None:
+            out = (torch.empty(n, C_, D, dtype=self.dtype).pin_memory(), torch.empty(n, C_, dtype=self.dtype).pin_memory())
+        draws_h, logp_h = out
+        for name, t, shape in (("theta_host", theta_host, (C_, D)), ("out[0]", draws_h, (n, C_, D)),
+                               ("out[1]", logp_h, (n, C_))):
+            if t is not None and (tuple(t.shape) != shape or t.dtype != self.dtype or t.is_cuda
+                                  or not t.is_contiguous()):
+                raise ValueError(f"{name} must be a contiguous host {self.dtype} tensor of shape {shape}")
+        if isinstance(chunk_chains, (list, tuple)):
+            sizes = [int(c) for c in chunk_chains]
+            if any(c <= 0 for c in sizes) or sum(sizes) != C_:
+                raise ValueError(f"chunk sizes must be positive and sum to {C_}")
+        else:
+            if chunk_chains is None:
+                chunk_chains = max(256, int(round(9472 * 1000 / max(D, 1) / 256)) * 256)
+            chunk_chains = max(1, min(int(chunk_chains), C_))
+            sizes = [min(chunk_chains, C_ - c) for c in range(0, C_, chunk_chains)]
+        cmax = max(sizes)
+        ring = getattr(self, "_hn_ring", None)
+        if ring is None or ring[0][0].shape[0] < n or ring[0][0].shape[1] < cmax:
+            ring = [(torch.empty(n, cmax, D, dtype=self.dtype, device=self.device),
+                     torch.empty(n, cmax, dtype=self.dtype, device=self.device),
+                     torch.empty(n, cmax, dtype=torch.int32, device=self.device)) for _ in range(3)]
+            self._hn_ring = ring
+        if getattr(self, "_hs", None) is None:
+            self._hs = tuple(torch.cuda.Stream(self.device) for _ in range(3))
+        s_in, s_run, s_out = self._hs
+        cur = torch.cuda.current_stream(self.device)
+        for st in self._hs:
+            st.wait_stream(cur)
+        stale = theta_host is not None or not self._cache_valid.value
+        acc_all = torch.empty(n, C_, dtype=torch.int32, device=self.device)
+        freed = [None, None, None]      # event: the ring slot's previous contents have left for the host
+        c0 = 0
+        for k, cn in enumerate(sizes):
+            slot = k % 3
+            valid = L.i32(0 if stale else 1)
+            if theta_host is not None:
+                with torch.cuda.stream(s_in):
+                    self._theta[c0:c0 + cn].copy_(theta_host[c0:c0 + cn], non_blocking=True)
+                s_run.wait_stream(s_in)
+            if freed[slot] is not None:
+                s_run.wait_event(freed[slot])
+            # staging laid out [n, cn, D] for THIS chunk (the kernels see cn chains)
+            sd = ring[slot][0].view(-1)[: n * cn * D].view(n, cn, D)
+            sl = ring[slot][1].view(-1)[: n * cn].view(n, cn)
+            sa = ring[slot][2].view(-1)[: n * cn].view(n, cn)
+            with torch.cuda.stream(s_run):
+                rng = make_rng(self._seed, self._t, self._chain_offset + c0, None, None, self._n_uniform)
+                o = L.DrawOut(sd.data_ptr(), sl.data_ptr(), sa.data_ptr())
+                self._launch(n, rng, o, c0, cn, valid)
+                acc_all[:, c0:c0 + cn].copy_(sa, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(s_run)
+            s_out.wait_event(done)
+            with torch.cuda.stream(s_out):
+                for t in range(n):
+                    draws_h[t, c0:c0 + cn].copy_(sd[t], non_blocking=True)
+                    logp_h[t, c0:c0 + cn].copy_(sl[t], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_out)
+                freed[slot] = ev
+            c0 += cn
+        self._t += n
+        self.last_accept = acc_all
+        self._cache_valid.value = 1
+        cur.wait_stream(s_run)
+        s_out.synchronize()
+        return draws_h, logp_h
+
     def _launch(self, n, rng, out, c0=0, cn=None, cache_valid=None):  # pragma: no cover - overridden
         raise NotImplementedError
 

@@ -97,18 +97,20 @@ class DrGhmcDiag(ChainSampler):
                 raise ValueError(f"each {item} in {name} must be positive, but found {item} of {v} "
                                  f"at index {idx}")
 
-    def sample_host(self, *a, **k):
-        raise NotImplementedError("sample_host: DrGhmcDiag keeps a persistent momentum per chain; "
-                                  "use sample()/sample_n() with device tensors")
-
-    def _launch(self, n, rng, out):
+    def _launch(self, n, rng, out, c0=0, cn=None, cache_valid=None):
+        """``c0, cn``: a chunk of chains (``sample_host`` pipelines chunks over PCIe); the persistent momentum of the
+        chunk's chains stays on the device, exactly as ``_rho`` is internal state upstream (drghmc.py:77,388)."""
         lib = L.lib()
-        used = torch.empty(n, self._C, dtype=torch.int32, device=self.device)
-        wp, wn = self._ws.get(lib.bk_drghmc_workspace_bytes(self._model.handle, self._C,
-                                                            self._max_proposals))
+        cn = self._C if cn is None else cn
+        if c0 == 0:
+            self._used = torch.empty(n, self._C, dtype=torch.int32, device=self.device)
+        used = self._used if cn == self._C else torch.empty(n, cn, dtype=torch.int32, device=self.device)
+        wp, wn = self._ws.get(lib.bk_drghmc_workspace_bytes(self._model.handle, cn, self._max_proposals))
         L.check(lib.bk_drghmc_sample(
-            self._model.handle, self._theta.data_ptr(), self._rho.data_ptr(), self._C,
+            self._model.handle, self._theta[c0:].data_ptr(), self._rho[c0:].data_ptr(), cn,
             self._max_proposals, self._sizes, self._counts, float(self._damping),
             1 if self._prob_retry else 0, ptr(self._metric), n, C.byref(rng), C.byref(out),
             used.data_ptr(), wp, wn, stream_ptr(self.device)))
-        self.last_n_uniform = used[:, 0] if self._single else used
+        if cn != self._C:
+            self._used[:, c0:c0 + cn].copy_(used)
+        self.last_n_uniform = self._used[:, 0] if self._single else self._used

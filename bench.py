@@ -6,13 +6,16 @@
 Workload (BASELINE.json configs[1]): HMCDiag, L=10
 leapfrog steps, 65,536 chains PER GPU on the 1000-dim dense-precision Gaussian
 (P = A A^T / D + I, A ~ N(0,1) from default_rng(0)); synthetic data, fp32
-device-Philox mode.  One "step" = one sample() of every chain (one chain-step
-per chain).  Chains shard across ranks with no communication (weak scaling).
+device-Philox mode.  One "step" = one sample_n(16) call: 16 draws of every chain
+(1,048,576 chain-steps per GPU; 20 steps ~ 1 s of device time).  Chains shard across
+ranks with no communication (weak scaling).
 
 Prints ONE JSON line (rank 0).  `value` = chain-steps/s with the chain state
 resident in HBM; `e2e` = the same metric through the public Python API with
 HOST buffers (pinned host -> device copy of the chain state and device -> host
-copy of the draw + log density inside the timed region, every step).
+copy of every draw + log density inside the timed region, every step).
+`config.secondary` carries the other BASELINE configs (c1, c3, c4 strong / weak
+over the N ranks, c5, MALA on c2), each with its own roofline fraction.
 """
 from __future__ import annotations
 
@@ -167,6 +170,25 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------
+DRAWS_PER_STEP = 16   # one step = one sample_n(16) call for every chain: 20 steps ~ 1 s of device time
+
+
+def bind_to_gpu_numa(local):
+    """Run this rank (and first-touch its pinned buffers) on the cores next to its GPU."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cores = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return len(allowed)
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -174,7 +196,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
+    ap.add_argument("--draws-per-step", type=int, default=DRAWS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the c1 / c3 / c4 / c5 / MALA legs")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="chains per sample_host chunk (0: library default)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -192,6 +216,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    n_cores = bind_to_gpu_numa(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -201,7 +226,7 @@ def main():
     from bayes_kit_b200 import _lib
     lib = _lib.lib()
 
-    C = args.chains
+    C, n = args.chains, args.draws_per_step
     model = bk.DensePrecGauss(c2_precision(), dtype=torch.float32, device=dev)
     # theta0 ~ N(0, I) per chain (the reference's default init, hmc.py:27); global chain ids
     sampler = bk.HMCDiag(model, EPS, L, chains=C, seed=0, chain_offset=rank * C)
@@ -211,9 +236,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def rank_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
     # ---- device-resident throughput ------------------------------------------------
     for _ in range(args.warmup):
-        sampler.sample_n(1)
+        sampler.sample_n(n)
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -221,12 +252,10 @@ def main():
     lib.bk_profile_enable(1)
     launches0 = lib.bk_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    acc_sum = 0.0
     ev0.record()
     for _ in range(args.steps):
-        # every step writes a fresh 262 MB draw (> L2) and streams ~1.6 GB of state
-        sampler.sample_n(1)
-        acc_sum += 0.0
+        # every draw streams ~1.6 GB of chain state (>> L2) and a step writes a fresh 16 x 262 MB draw block
+        sampler.sample_n(n)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -238,41 +267,81 @@ def main():
     lib.bk_profile_read(_lib.PROF_STEP, sms_, sn)
     accept = float(sampler.last_accept.float().mean())
     clk = clocks.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t)
-    value = world * C * args.steps / (ms_max * 1e-3)
+    ms_max = rank_max(ms)
+    value = world * C * n * args.steps / (ms_max * 1e-3)
 
     # ---- end to end through the public API with host buffers --------------------------
-    # two pinned host buffers: step k reads the chain state from one and returns the
-    # draw in the other, which is the next step's input (no host-side memcpy)
-    host_buf = [torch.empty(C, D, dtype=torch.float32).pin_memory() for _ in range(2)]
-    host_buf[0].copy_(sampler.theta)
-    host_lp = torch.empty(C, dtype=torch.float32).pin_memory()
+    # One step = the call a user of the reference makes for n draws of every chain, host arrays in and out
+    # (hmc.py:55-63 returns host arrays): the chain state is uploaded from pinned host memory (the previous
+    # step's last draw), all n draws + log densities come back into pinned host memory.
+    host_draws = torch.empty(n, C, D, dtype=torch.float32, pin_memory=True)
+    host_lp = torch.empty(n, C, dtype=torch.float32, pin_memory=True)
+    host_draws[n - 1].copy_(sampler.theta)
     e2e_steps = max(3, min(args.steps, 10))
 
-    def e2e_step(k):
-        # public API: chain state in from host buffer k&1, draw + log density out to the other;
-        # H2D, kernels and D2H of successive chain chunks overlap on three streams
-        sampler.sample_host(host_buf[k & 1], out=(host_buf[(k + 1) & 1], host_lp),
-                            chunk_chains=args.e2e_chunk or None)
+    def e2e_step():
+        # next step's input = this step's last draw, read in place from the pinned result buffer (a chunk's
+        # rows are uploaded before that chunk's draws are written back, so the aliasing is safe)
+        sampler.sample_host_n(n, host_draws[n - 1], out=(host_draws, host_lp), chunk_chains=args.e2e_chunk or None)
 
-    for k in range(2):
-        e2e_step(k)
+    for _ in range(2):
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        e2e_step(k)
+    for _ in range(e2e_steps):
+        e2e_step()
     barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * C * e2e_steps / float(t)
+    e2e_s = rank_max(time.perf_counter() - t0)
+    e2e_value = world * C * n * e2e_steps / e2e_s
+    # the box's copy floor for exactly these bytes: all ranks copy one step's D2H volume at the same time
+    # (pinned, one stream per rank) -- the e2e step cannot finish faster than this on this box
+    dsrc = torch.empty(C, D, dtype=torch.float32, device=dev)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        for t in range(n):
+            host_draws[t].copy_(dsrc, non_blocking=True)
+    barrier()
+    floor_s = rank_max((time.perf_counter() - t0) / 2)
+    del dsrc
+
+    # ---- secondary workloads (all ranks take part in the sharded ones) ------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_bw = peaks.get("hbm_gbs") or 6650.0               # fallback: B200_PROFILING.md
+    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    secondary = {}
+    if not args.no_secondary:
+        del host_draws
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import bench_legs as legs
+        torch.cuda.empty_cache()
+        for name, fn in (("c4_strong", lambda: legs.leg_c4(rank, world, peak_bw, weak=False)),
+                         ("c4_weak", lambda: legs.leg_c4(rank, world, peak_bw, weak=True)),
+                         ("c3", lambda: legs.leg_c3(rank, world, peak_tf))):
+            if name == "c4_weak" and world == 1:
+                continue
+            try:
+                secondary[name] = fn()
+            except Exception as e:      # a failed leg must not lose the headline
+                secondary[name] = {"error": repr(e)}
+            torch.cuda.empty_cache()
+        if rank == 0:
+            for name, fn in (("c1", lambda: legs.leg_c1(peak_bw)), ("c2_mala", lambda: legs.leg_c2_mala(peak_bw, peak_tf)),
+                             ("c5", lambda: legs.leg_c5(peak_bw))):
+                try:
+                    secondary[name] = fn()
+                except Exception as e:
+                    secondary[name] = {"error": repr(e)}
+                torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
@@ -291,33 +360,38 @@ def main():
 
     # ---- roofline of the dominant kernel -----------------------------------------------
     # k_dense_tc in STEP mode (gradient GEMM + fused leapfrog update): L-1 of the L
-    # gradient launches of a step and ~3/4 of its time.  It is HBM-bound: SURVEY 8(d)
+    # gradient launches of a draw and ~2/3 of its time.  It is HBM-bound: SURVEY 8(d)
     # c2 "HBM side" = 4*D*s bytes per chain per leapfrog step (theta, rho round trip).
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak_bw = peaks.get("hbm_gbs") or 6650.0               # fallback: B200_PROFILING.md
-    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
-    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     # one persistent STEP launch fuses the interior leapfrog steps of a draw (L-1 of them at c2); algorithmic
     # bytes per launch = 16 B per chain-dim-step x the steps that launch ran
-    steps_per_launch = (L - 1) * args.steps / max(sn.value, 1)
+    n_draws_timed = n * args.steps
+    steps_per_launch = (L - 1) * n_draws_timed / max(sn.value, 1)
     bytes_per_launch = 4.0 * D * 4 * C * steps_per_launch   # 16 KB per chain-leapfrog-step
     s_avg_ms = sms_.value / max(sn.value, 1)
     g_avg_ms = gms.value / max(gn.value, 1)
     achieved = bytes_per_launch / (s_avg_ms * 1e-3) / 1e9 if sn.value else None
+    # DRAM bytes of one launch from the committed ncu --set full capture of this kernel (never a constant typed
+    # into this file): profiles/ncu_traffic.json, written by scripts/summarize_ncu.py from the .ncu-rep
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k_dense_tc_step"]
+        if C == tj["chains"] and abs(steps_per_launch - tj["leapfrog_steps_per_launch"]) < 1e-9:
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_bw, "unit": "GB/s",
                 "frac": (achieved / peak_bw) if achieved else None,
-                # ncu --set full (profiles/r1_ncu_k_dense_tc.md): dram read + write of one fused launch = 9.81 GB for
-                # 9 leapfrog steps (incl. the bf16 operand copy and the pad dims 1000..1023) = 1.090 GB per step
-                "traffic": 1.090e9 * steps_per_launch if C == CHAINS_PER_GPU else None,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": "k_dense_tc STEP mode (tcgen05 gradient GEMM + fused leapfrog epilogue, "
                           "persistent over the interior leapfrog steps of a draw)",
                 "leapfrog_steps_per_launch": steps_per_launch,
                 "launches_timed": int(sn.value), "avg_launch_ms": s_avg_ms,
                 "share_of_step": sms_.value / ms if ms else None, "peak_source": peak_src,
+                "whole_step": {  # every kernel of a draw, on the algorithmic bytes of the whole draw:
+                    # 16 B x C x D per interior leapfrog step + begin (18 B) + end (24 B) + GRAD operand/gradient (10 B)
+                    "bytes_per_draw": (16.0 * (L - 1) + 18 + 24 + 10) * C * D,
+                    "achieved": (16.0 * (L - 1) + 18 + 24 + 10) * C * D * n_draws_timed / (ms * 1e-3) / 1e9,
+                    "frac": (16.0 * (L - 1) + 18 + 24 + 10) * C * D * n_draws_timed / (ms * 1e-3) / 1e9 / peak_bw},
                 "tensor_side": {  # the endpoint gradient (3-pass bf16 split) is tensor-bound
                     "kernel": "k_dense_tc GRAD mode", "flops_per_launch": 3 * 2.0 * C * D * D,
                     "avg_launch_ms": g_avg_ms, "launches_timed": int(gn.value),
@@ -332,18 +406,29 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"c2: HMCDiag L={L} eps={EPS}, {C} chains/GPU x {D}-dim dense-precision "
-                               f"Gaussian (P=AA^T/D+I, seed 0), device Philox",
-                   "chains_per_gpu": C, "dims": D, "leapfrog_steps": L, "accept_rate": accept,
+                               f"Gaussian (P=AA^T/D+I, seed 0), device Philox; one step = sample_n({n}): "
+                               f"{n} draws of every chain",
+                   "chains_per_gpu": C, "dims": D, "leapfrog_steps": L, "draws_per_step": n,
+                   "chain_steps_per_step": world * C * n, "ms_per_draw": ms_max / args.steps / n,
+                   "timed_region_s": ms_max * 1e-3, "accept_rate": accept,
                    "grad_evals_per_s": value * L, "min_ess_per_s": value * ess_per_step,
                    "ess_per_chain_step_min_param": ess_per_step,
-                   "l2": "inputs larger than L2 (>= 1.5 GB of chain state streamed per step)"},
+                   "l2": "inputs larger than L2 (>= 1.5 GB of chain state streamed per draw)",
+                   "cpu_cores_bound_to_gpu_numa": n_cores,
+                   "secondary": secondary},
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": C * D * 4,
-                "d2h_bytes_per_step": C * D * 4 + C * 4, "steps": e2e_steps},
+                "d2h_bytes_per_step": n * (C * D * 4 + C * 4), "steps": e2e_steps,
+                "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                "api": f"HMCDiag.sample_host_n({n}, theta_host, out=(draws_host, logp_host))",
+                # this box's D2H copy time for one step's draws with all ranks copying at once
+                "d2h_copy_floor_ms": 1e3 * floor_s,
+                "floor_frac": floor_s / (e2e_s / e2e_steps)},
         "gpu_launches": int(launches), "clocks": clk,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
