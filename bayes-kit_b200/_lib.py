@@ -46,7 +46,11 @@ class SmcShard(C.Structure):
 
 
 class DrawOut(C.Structure):
-    _fields_ = [("draws", vp), ("logp", vp), ("accept", vp)]
+    _fields_ = [("draws", vp), ("logp", vp), ("accept", vp), ("layout", i32), ("mom_mean", vp), ("mom_m2", vp),
+                ("mom_n0", i64)]
+
+
+DRAWS_NCD, DRAWS_CDN = 0, 1
 
 
 class SeriesLayout(C.Structure):

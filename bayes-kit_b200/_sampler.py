@@ -82,21 +82,42 @@ class ChainSampler:
     def theta(self) -> torch.Tensor:
         return self._theta[0] if self._single else self._theta
 
-    def sample_n(self, n: int, normals=None, uniforms=None, keep_draws: bool = True, moments: bool = False):
+    def _fuses_extras(self) -> bool:
+        """True when this sampler's engine folds streaming moments / writes series-major draws inside its own
+        kernel: the fp32 register-resident samplers of the iso / diagonal Gaussian plugins (bk.h: bk_draw_out)."""
+        from .models import DiagGauss, IsoGauss
+        import os
+        return (self.dtype == torch.float32 and isinstance(self._model, (IsoGauss, DiagGauss)) and self._dim <= 512
+                and os.environ.get("BK_FORCE_GENERIC", "0") != "1" and type(self).__name__ != "DrGhmcDiag")
+
+    def sample_n(self, n: int, normals=None, uniforms=None, keep_draws: bool = True, moments: bool = False,
+                 layout: str = "draws"):
         """Advance every chain n draws in one call.  Returns (draws [n, C, D],
         logp [n, C]) ([n, D], [n] for a single chain); with keep_draws=False only
         the final state is kept (warm-up) and draws is None.  ``moments=True``
         folds the batch into running per-chain, per-dimension mean / variance
         (``running_moments()``, ``running_rhat()``) -- convergence monitoring
-        without storing or re-reading the chains."""
+        without storing or re-reading the chains: the fused fp32 samplers accumulate in
+        registers inside the sampling kernel (no second pass), the GEMM engines fold the
+        draws they wrote.  ``layout="series"`` (fused fp32 samplers): draws come back as
+        [C, D, n] -- every (chain, dim) series contiguous over the draws, the layout
+        ``ess`` / ``iat`` / ``autocorr`` stream without a transposition."""
         n = int(n)
         C_, D = self._C, self._dim
-        if moments and not keep_draws and n > 16:      # bound the transient draw buffer
+        if layout not in ("draws", "series"):
+            raise ValueError("layout must be 'draws' ([n, C, D]) or 'series' ([C, D, n])")
+        fused = self._fuses_extras()
+        if layout == "series" and not fused:
+            raise NotImplementedError("layout='series' is written by the fused fp32 samplers of the iso / diagonal "
+                                      "Gaussian plugins; other engines return [n, C, D] (diagnostics read it in place)")
+        need_buf = keep_draws or (moments and not fused)
+        if moments and not keep_draws and not fused and n > 16:      # bound the transient draw buffer
             out_l = []
             for k in range(0, n, 16):
                 out_l.append(self.sample_n(min(16, n - k), keep_draws=False, moments=True)[1])
             return None, torch.cat(out_l)
-        draws = torch.empty(n, C_, D, dtype=self.dtype, device=self.device) if (keep_draws or moments) else None
+        shape = (C_, D, n) if layout == "series" else (n, C_, D)
+        draws = torch.empty(*shape, dtype=self.dtype, device=self.device) if need_buf else None
         logp = torch.empty(n, C_, dtype=self.dtype, device=self.device)
         acc = torch.empty(n, C_, dtype=torch.int32, device=self.device)
         if normals is not None:
@@ -104,23 +125,29 @@ class ChainSampler:
             uniforms = to_dev(uniforms, self.dtype, self.device).reshape(n, C_, self._n_uniform)
         rng = make_rng(self._seed, self._t, self._chain_offset, normals, uniforms, self._n_uniform)
         out = L.DrawOut(ptr(draws), logp.data_ptr(), acc.data_ptr())
-        with torch.cuda.device(self.device):
-            self._launch(n, rng, out)
-        self._t += n
-        self.last_accept = acc[:, 0] if self._single else acc
+        out.layout = L.DRAWS_CDN if layout == "series" else L.DRAWS_NCD
         if moments and n > 0:
             if getattr(self, "_mom", None) is None:
                 self._mom = [torch.empty(C_, D, dtype=torch.float64, device=self.device),
                              torch.empty(C_, D, dtype=torch.float64, device=self.device), 0]
-            with torch.cuda.device(self.device):
+            if type(self).__name__ != "DrGhmcDiag":       # folded by the library (in-kernel where the engine fuses it)
+                out.mom_mean, out.mom_m2, out.mom_n0 = self._mom[0].data_ptr(), self._mom[1].data_ptr(), self._mom[2]
+        with torch.cuda.device(self.device):
+            self._launch(n, rng, out)
+            if moments and n > 0 and type(self).__name__ == "DrGhmcDiag":
                 L.check(L.lib().bk_moments_accumulate(
                     draws.data_ptr(), L.BK_F32 if self.dtype == torch.float32 else L.BK_F64, n, C_ * D,
                     self._mom[2], self._mom[0].data_ptr(), self._mom[1].data_ptr(), stream_ptr(self.device)))
+        self._t += n
+        self.last_accept = acc[:, 0] if self._single else acc
+        if moments and n > 0:
             self._mom[2] += n
             if not keep_draws:
                 draws = None
         if self._single:
-            return (draws[:, 0] if draws is not None else None), logp[:, 0]
+            if draws is not None:
+                draws = draws[0] if layout == "series" else draws[:, 0]
+            return draws, logp[:, 0]
         return draws, logp
 
     def running_moments(self):

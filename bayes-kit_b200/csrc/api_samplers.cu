@@ -56,6 +56,10 @@ void fill_sep(SepArgs<T>& a, const Model& m, void* theta, int64_t C, const void*
     a.draws = (T*)out.draws;
     a.logp = (T*)out.logp;
     a.accept = out.accept;
+    a.layout = out.layout;
+    a.mom_mean = out.mom_mean;
+    a.mom_m2 = out.mom_m2;
+    a.mom_n0 = out.mom_n0;
     bool al = ptr_aligned16(theta) && ptr_aligned16(out.draws) && ptr_aligned16(m.d.mu) &&
               ptr_aligned16(m.d.prec) && ptr_aligned16(metric) &&
               (rng->mode != BK_RNG_INJECTED || ptr_aligned16(rng->normals));
@@ -170,6 +174,24 @@ size_t sampler_ws(uint64_t h, int64_t C) {
     return m->d.dtype == BK_F64 ? generic_ws_bytes<double>(*m, C) : generic_ws_bytes<float>(*m, C);
 }
 
+// Streaming moments / series-major draws (bk_draw_out) are fused into the fp32 register-resident kernels; every
+// other engine folds the draws it wrote in a second pass and cannot write the series-major layout.
+// fused_extras: true when this call's engine handles bk_draw_out's extras itself.
+bool fused_extras(const Model& m) { return m.d.dtype == BK_F32 && use_fused<float>(m); }
+
+int check_extras(const Model& m, const bk_draw_out& o, const char* who) {
+    if (fused_extras(m)) return BK_OK;
+    BK_CHECK_ARG(o.layout == BK_DRAWS_NCD || !o.draws,
+                 "%s: the series-major draw layout is written by the fused fp32 separable samplers only", who);
+    BK_CHECK_ARG(!o.mom_mean || o.draws, "%s: streaming moments on this engine fold the stored draws -- pass draws", who);
+    return BK_OK;
+}
+
+int finish_extras(const Model& m, const bk_draw_out& o, int64_t C, int64_t n, void* stream) {
+    if (fused_extras(m) || !o.mom_mean) return BK_OK;
+    return bk_moments_accumulate(o.draws, m.d.dtype, n, C * m.d.dims, o.mom_n0, o.mom_mean, o.mom_m2, stream);
+}
+
 }  // namespace
 
 extern "C" {
@@ -190,11 +212,14 @@ int bk_hmc_diag_sample(uint64_t handle, void* theta, void* lp_cache, void* grad_
     if (rc) return rc;
     bk_draw_out o = out ? *out : bk_draw_out{nullptr, nullptr, nullptr};
     if (C == 0 || n_draws == 0) return BK_OK;
+    if ((rc = check_extras(*m, o, "bk_hmc_diag_sample"))) return rc;
     if (m->d.dtype == BK_F64)
-        return hmc_t<double>(*m, theta, lp_cache, grad_cache, cache_valid_host, C, stepsize, steps,
+        rc = hmc_t<double>(*m, theta, lp_cache, grad_cache, cache_valid_host, C, stepsize, steps,
                              metric, n_draws, rng, o, ws, ws_bytes, (cudaStream_t)stream);
-    return hmc_t<float>(*m, theta, lp_cache, grad_cache, cache_valid_host, C, stepsize, steps, metric,
+    else
+        rc = hmc_t<float>(*m, theta, lp_cache, grad_cache, cache_valid_host, C, stepsize, steps, metric,
                         n_draws, rng, o, ws, ws_bytes, (cudaStream_t)stream);
+    return rc ? rc : finish_extras(*m, o, C, n_draws, stream);
 }
 
 int bk_mala_sample(uint64_t handle, void* theta, void* lp_cache, void* grad_cache,
@@ -209,11 +234,14 @@ int bk_mala_sample(uint64_t handle, void* theta, void* lp_cache, void* grad_cach
     if (rc) return rc;
     bk_draw_out o = out ? *out : bk_draw_out{nullptr, nullptr, nullptr};
     if (C == 0 || n_draws == 0) return BK_OK;
+    if ((rc = check_extras(*m, o, "bk_mala_sample"))) return rc;
     if (m->d.dtype == BK_F64)
-        return mala_t<double>(*m, theta, lp_cache, grad_cache, cache_valid_host, C, epsilon, n_draws,
+        rc = mala_t<double>(*m, theta, lp_cache, grad_cache, cache_valid_host, C, epsilon, n_draws,
                               rng, o, ws, ws_bytes, (cudaStream_t)stream);
-    return mala_t<float>(*m, theta, lp_cache, grad_cache, cache_valid_host, C, epsilon, n_draws, rng,
+    else
+        rc = mala_t<float>(*m, theta, lp_cache, grad_cache, cache_valid_host, C, epsilon, n_draws, rng,
                          o, ws, ws_bytes, (cudaStream_t)stream);
+    return rc ? rc : finish_extras(*m, o, C, n_draws, stream);
 }
 
 int bk_mh_rw_sample(uint64_t handle, void* theta, void* lp_cache, int32_t* cache_valid_host,
@@ -227,11 +255,14 @@ int bk_mh_rw_sample(uint64_t handle, void* theta, void* lp_cache, int32_t* cache
     if (rc) return rc;
     bk_draw_out o = out ? *out : bk_draw_out{nullptr, nullptr, nullptr};
     if (C == 0 || n_draws == 0) return BK_OK;
+    if ((rc = check_extras(*m, o, "bk_mh_rw_sample"))) return rc;
     if (m->d.dtype == BK_F64)
-        return mh_t<double>(*m, theta, lp_cache, cache_valid_host, C, scale, hastings, n_draws, rng, o,
+        rc = mh_t<double>(*m, theta, lp_cache, cache_valid_host, C, scale, hastings, n_draws, rng, o,
                             ws, ws_bytes, (cudaStream_t)stream);
-    return mh_t<float>(*m, theta, lp_cache, cache_valid_host, C, scale, hastings, n_draws, rng, o, ws,
+    else
+        rc = mh_t<float>(*m, theta, lp_cache, cache_valid_host, C, scale, hastings, n_draws, rng, o, ws,
                        ws_bytes, (cudaStream_t)stream);
+    return rc ? rc : finish_extras(*m, o, C, n_draws, stream);
 }
 
 }  // extern "C"

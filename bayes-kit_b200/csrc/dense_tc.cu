@@ -272,6 +272,8 @@ struct StepArgs {
     // spin (acquire) until it reaches m_tiles * EPI_WARPS.  Zeroed by the host before the launch.
     int n_steps;
     uint32_t* sync;
+    uint32_t* err;        // set to 1 when a producer gave up waiting (fused grid not co-resident): the end kernel
+                          // then reports NaN log densities instead of the launch hanging
     float* g_out;         // [C, D] row-major, or tile-blocked when g_blocked
     int g_blocked;
     int debug;            // BK_TC_DEBUG bits: 1 = skip TMA+MMA, 2 = skip epilogue global traffic, 4 = load B on even stages only,
@@ -371,7 +373,24 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                 const int64_t n_tile = tile / m_units;
                 if (step > 0) {      // every dim-tile of this chain-tile has written the previous step's operand
                     const uint32_t* flag = a.sync + (int64_t)(step - 1) * a.n_tiles + n_tile;
-                    while (ld_acquire_gpu(flag) < sync_full) __nanosleep(64);
+                    if (ld_acquire_gpu(flag) < sync_full) {
+                        // bounded: the fused grid's co-residency rests on an occupancy query, not on a cooperative
+                        // launch; if another long-lived kernel holds SMs the wait gives up after ~4 s
+                        uint64_t t_start;
+                        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
+                        unsigned spins = 0;
+                        while (ld_acquire_gpu(flag) < sync_full) {
+                            __nanosleep(64);
+                            if ((++spins & 4095u) == 0) {
+                                uint64_t t_now;
+                                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_now));
+                                if (t_now - t_start > 4000000000ull || (a.err && *(volatile uint32_t*)a.err)) {
+                                    if (a.err) atomicExch(a.err, 1u);
+                                    break;
+                                }
+                            }
+                        }
+                    }
                     fence_proxy_async_all();     // generic-proxy writes (other CTAs) -> this thread's TMA reads
                 }
                 for (int it = 0; it < iters; ++it) {
@@ -744,6 +763,7 @@ struct HmcTcArgs {
     float *draws, *logp;
     int32_t* accept;
     int out_lp;                 // 1: report log p(theta) (MALA, mala.py:66) instead of the joint (hmc.py:63)
+    const uint32_t* err;        // fused STEP launch gave up waiting (see StepArgs::err): report NaN
 };
 
 // One warp per chain, lane-strided blocks of 4 elements (the Philox block
@@ -863,8 +883,9 @@ __global__ void __launch_bounds__(256) k_hmc_end_tc(HmcTcArgs p, int64_t t) {
     }
     kin = warp_sum(kin);
     dot = warp_sum(dot);
-    const float lpq = 0.5f * dot;
-    const float h1 = lpq - 0.5f * kin, h0 = p.h0[c];
+    const bool lost = p.err && *p.err != 0u;
+    const float lpq = lost ? __int_as_float(0x7fc00000) : 0.5f * dot;
+    const float h1 = lpq - 0.5f * kin, h0 = lost ? lpq : p.h0[c];
     float u;
     if (p.rng.mode == BK_RNG_INJECTED)
         u = reinterpret_cast<const float*>(p.rng.uniforms)[(t * p.C + c) * p.rng.n_uniform];
@@ -940,7 +961,16 @@ constexpr int MAX_FUSED_STEPS = 64;     // sync counters reserved in the workspa
 // grid co-resident (the producers spin on counters other clusters advance).  1 = launch per step.
 // BK_TC_FUSE=0 (diagnostic) forces 1.
 static int max_fused_steps(int m_tiles, int debug) {
-    static int fuse_env = -1, pair_env = -1, clusters = -1, sms = 0;
+    static int fuse_env = -1, pair_env = -1;
+    static int clusters_dev[64], sms_dev[64];
+    static bool dev_init = false;
+    static std::mutex dev_mu;
+    std::lock_guard<std::mutex> dev_lock(dev_mu);
+    if (!dev_init) { for (int i = 0; i < 64; ++i) { clusters_dev[i] = -1; sms_dev[i] = 0; } dev_init = true; }
+    int cur_dev = 0;
+    if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= 64) return 1;
+    int& clusters = clusters_dev[cur_dev];      // occupancy and SM count are per DEVICE, not per process
+    int& sms = sms_dev[cur_dev];
     if (fuse_env < 0) { const char* e = getenv("BK_TC_FUSE"); fuse_env = (e && e[0] == '0') ? 0 : 1; }
     if (pair_env < 0) { const char* e = getenv("BK_TC_PAIR"); pair_env = (e && e[0] == '0') ? 0 : 1; }
     if (!fuse_env || !pair_env || m_tiles % 2 != 0 || (debug & 4)) return 1;
@@ -969,7 +999,12 @@ static int max_fused_steps(int m_tiles, int debug) {
 
 static int launch_tc(const Model& m, const StepArgs& a, const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo,
                      cudaStream_t st) {
-    static bool attr = false;
+    static bool attr_dev[64] = {false};
+    static int sms_by_dev[64] = {0};
+    int launch_dev = 0;
+    BK_CUDA(cudaGetDevice(&launch_dev));
+    if (launch_dev < 0 || launch_dev >= 64) { set_error("device index %d out of range", launch_dev); return BK_E_CUDA; }
+    bool& attr = attr_dev[launch_dev];          // function attributes are per device
     if (!attr) {
         BK_CUDA(cudaFuncSetAttribute(k_dense_tc<TC_MODE_STEP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg<TC_MODE_STEP, false>::SMEM_BYTES));
@@ -986,12 +1021,8 @@ static int launch_tc(const Model& m, const StepArgs& a, const __nv_bfloat16* b_h
     static int pair_env = -1;
     if (pair_env < 0) { const char* e = getenv("BK_TC_PAIR"); pair_env = (e && e[0] == '0') ? 0 : 1; }
     const bool pair = pair_env && a.m_tiles % 2 == 0 && !(a.debug & 4);
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        BK_CUDA(cudaGetDevice(&dev));
-        BK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    int& sms = sms_by_dev[launch_dev];
+    if (!sms) BK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, launch_dev));
     CUtensorMap mA0, mA1, mB0, mB1;
     int rc;
     const int bk = a.mode == TC_MODE_STEP ? Cfg<TC_MODE_STEP>::KS : Cfg<TC_MODE_GRAD>::KS;
@@ -1114,7 +1145,7 @@ size_t dense_tc_hmc_ws_bytes(const Model& m, int64_t C) {
     // q, r, gq fp32; h0; q_hi x2, q_lo bf16; eval scratch for the cache refresh
     const size_t n_tiles = align_up((size_t)C, tc::BN) / tc::BN;
     return 3 * align_up(n * 4, 256) + align_up((size_t)C * 4, 256) + 3 * align_up(nb * 2, 256) +
-           align_up(tc::MAX_FUSED_STEPS * n_tiles * 4, 256) + model_eval_ws_bytes(m, C) + 2048;
+           align_up(tc::MAX_FUSED_STEPS * n_tiles * 4 + 256, 256) + model_eval_ws_bytes(m, C) + 2048;
 }
 
 // gradient of the dense plugin on tensor cores (3-pass split): theta [C,D] -> grad [C,D]
@@ -1148,7 +1179,8 @@ int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* 
     float* h0 = ar.take<float>(C);
     __nv_bfloat16* qhi[2] = {ar.take<__nv_bfloat16>(nb), ar.take<__nv_bfloat16>(nb)};
     __nv_bfloat16* qlo = ar.take<__nv_bfloat16>(nb);
-    uint32_t* sync = ar.take<uint32_t>(tc::MAX_FUSED_STEPS * (align_up((size_t)C, tc::BN) / tc::BN));
+    uint32_t* sync = ar.take<uint32_t>(tc::MAX_FUSED_STEPS * (align_up((size_t)C, tc::BN) / tc::BN) + 64);
+    uint32_t* err_word = sync + tc::MAX_FUSED_STEPS * (align_up((size_t)C, tc::BN) / tc::BN);
     const size_t ebytes = model_eval_ws_bytes(m, C);
     void* ews = ar.take<char>(ebytes);
     if (!ar.ok()) {
@@ -1171,8 +1203,11 @@ int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* 
     h.eps = (float)eps; h.half_eps = (float)(0.5 * eps); h.inv_eps = (float)(1.0 / eps); h.rng = *rng;
     h.draws = (float*)out.draws; h.logp = (float*)out.logp; h.accept = out.accept;
     h.out_lp = report_lp ? 1 : 0;
+    h.err = err_word;
+    BK_CUDA(cudaMemsetAsync(err_word, 0, sizeof(uint32_t), st));
     tc::StepArgs a;
     memset(&a, 0, sizeof(a));
+    a.err = err_word;
     a.C = C; a.D = D; a.Dp = (int)m.Dp;
     a.m_tiles = (int)(m.Dp / tc::BM); a.n_tiles = (C + tc::BN - 1) / tc::BN; a.kblocks = (int)(m.Dp / tc::BK);
     a.eps = (float)eps; a.metric = metric; a.cvec = (const float*)m.Pmu; a.g_out = gq;

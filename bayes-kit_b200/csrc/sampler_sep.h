@@ -28,6 +28,10 @@ struct SepArgs {
     T* draws;         // [n, C, D] or NULL
     T* logp;          // [n, C] or NULL
     int32_t* accept;  // [n, C] or NULL
+    int layout;       // BK_DRAWS_NCD / BK_DRAWS_CDN (series-major [C, D, n], staged through shared memory)
+    double* mom_mean; // [C, D] running mean (NULL: no streaming moments)
+    double* mom_m2;   // [C, D] running sum of squared deviations
+    int64_t mom_n0;   // draws the running moments already cover
 };
 
 template <typename T>

@@ -90,6 +90,7 @@ __device__ __forceinline__ uint64_t global_ns() {
 constexpr uint64_t BK_SMC_WAIT_NS = 20ull * 1000 * 1000 * 1000;
 __device__ __forceinline__ bool mail_wait(const uint64_t* flag, uint64_t step, uint64_t* mailbox) {
     if (ld_acquire_sys(flag) >= step) return true;
+    if (ld_relaxed_sys(mailbox + MB_ERR) == 1ull) return false;   // a wait already timed out: the run is lost, do not wait again
     const uint64_t t0 = global_ns();
     unsigned it = 0;
     while (ld_acquire_sys(flag) < step) {

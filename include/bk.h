@@ -91,11 +91,25 @@ typedef struct bk_rng {
     const void* uniforms;   /* INJECTED: [n_draws, C, n_uniform] uniforms in [0,1)       */
 } bk_rng;
 
+enum { BK_DRAWS_NCD = 0,  /* draws [n_draws, C, D]: one draw of every chain after the other      */
+       BK_DRAWS_CDN = 1   /* draws [C, D, n_draws]: every (chain, dim) SERIES contiguous over the
+                             draws -- what bk_iat_ess / bk_autocorr stream without a transposition
+                             (SURVEY 8(f)-2); fused separable samplers only                      */ };
+
 /* per-call outputs shared by the MCMC samplers; any pointer may be NULL */
 typedef struct bk_draw_out {
-    void*    draws;   /* [n_draws, C, D]                                                 */
+    void*    draws;   /* [n_draws, C, D] (or [C, D, n_draws], see layout)                */
     void*    logp;    /* [n_draws, C] value sample() returns (HMC/DrGHMC: JOINT logp)    */
     int32_t* accept;  /* [n_draws, C] 1 = proposal accepted                              */
+    int32_t  layout;  /* BK_DRAWS_*                                                      */
+    /* Streaming moments folded in the sampler's epilogue: running per-chain,
+     * per-dimension mean [C, D] and sum of squared deviations M2 [C, D] (fp64) that already cover
+     * mom_n0 draws are updated with this call's n_draws WITHOUT a pass over stored draws (the fused
+     * separable samplers accumulate in registers across the draws of the launch and merge once, Chan et
+     * al.); the other engines fold the draws they wrote (draws must be given).  NULL: off. */
+    double*  mom_mean;
+    double*  mom_m2;
+    int64_t  mom_n0;
 } bk_draw_out;
 
 BK_API const char* bk_last_error(void);

@@ -1,6 +1,7 @@
 """BASELINE.json's full sizes, checked through size-independent properties (the oracle finishes
-only small cases): c2 (65,536 chains x 1000-dim dense Gaussian, HMC and MALA), c4 (10^6 particles x
-50 dims x 100 temperatures).  c5's full size (32.8 GB of draws) runs in scripts/c5_full.py."""
+only small cases): c2 (65,536 chains x 1000-dim dense Gaussian, HMC and MALA), c3 (100k x 100 hierarchical
+logistic regression, 1024 chains = one GPU's share of the 8,192), c4 (10^6 particles x 50 dims x 100
+temperatures), c5 (8,192 chains x 10,000 draws x 100 params: 819,200 series, 32.8 GB of draws)."""
 import numpy as np
 import pytest
 import torch
@@ -30,8 +31,9 @@ def test_c2_full_size_hmc_and_mala(bk):
     # 65,536 independent chains after burn-in: cross-chain moments of one draw estimate the posterior
     x = np_(d2[0]).astype(np.float64)
     n = C
-    assert np.all(np.abs(x.mean(0)) <= 5 * np.sqrt(var / n))
-    assert np.all(np.abs(x.var(0, ddof=1) / var - 1) <= 5 * np.sqrt(2 / n))
+    # north_star: posterior means / variances within 4 MCSE (2000 comparisons at 4 sigma: the seed is fixed)
+    assert np.all(np.abs(x.mean(0)) <= 4 * np.sqrt(var / n))
+    assert np.all(np.abs(x.var(0, ddof=1) / var - 1) <= 4 * np.sqrt(2 / n))
     # joint log density = log p - kinetic; log p of a draw from N(0, P^-1) is -chi2_D / 2
     m = bk.MALA(model, 2e-3, init=d2[0], seed=1)
     dm, lpm = m.sample_n(3)
@@ -57,3 +59,121 @@ def test_c4_full_size_smc(bk):
         assert 0.1 < float(((w[:, None] * (th - mean) ** 2).sum(0)).mean()) < 0.35
         if "ess_threshold" in kw:
             assert 0 < sum(smc.resampled) < T
+
+
+def test_c3_full_shape_hier_logreg(bk):
+    """BASELINE configs[2] at its stated shape on one GPU's share: N = 100,000 observations x Dx = 100,
+    1024 chains (8,192 over 8 GPUs, X replicated, no communication).
+    (1) tcgen05 gradient and split-precision density vs the fp64 NumPy model on a chain subset;
+    (2) HMC accept rate in the tuned band;
+    (3) posterior means / variances of all 102 parameters: fp32 tensor-core run vs an fp64 run of the generic
+        engine (CUDA-core gradients, the parity path) from the same start, within 4 MCSE (MCSE from the device ESS)."""
+    from oracle.models import HierLogReg
+    N, Dx, C, L, eps = 100_000, 100, 1024, 10, 0.01
+    X, y = HierLogReg.c3_data(N, Dx, seed=0)
+    om = HierLogReg(X, y)
+    rng = np.random.default_rng(1)
+    th0 = (rng.normal(size=(C, Dx + 2)) * 0.1).astype(np.float32).astype(np.float64)
+    m32 = bk.HierLogReg(X, y, dtype=torch.float32)
+    # (1) gradients on a subset of chains
+    lp_f, g_f = m32.log_density_gradient(th0[:16], fast=True)
+    lp_p, g_p = m32.log_density_gradient(th0[:16])
+    want = [om.log_density_gradient(t) for t in th0[:16]]
+    wl, wg = np.array([w[0] for w in want]), np.stack([w[1] for w in want])
+    assert np.abs(np_(g_f) - wg).max() <= 1e-2 * np.abs(wg).max()          # bf16 operands, interior steps only
+    assert np.abs(np_(g_p) - wg).max() <= 2e-5 * np.abs(wg).max()          # precise path
+    np.testing.assert_allclose(np_(lp_p), wl, rtol=2e-6)                    # the density that enters the accept test
+    # (2) + (3)
+    n_burn, n_keep = 300, 400
+    s32 = bk.HMCDiag(m32, eps, L, init=th0, seed=0)
+    s32.sample_n(n_burn, keep_draws=False)
+    d32, _ = s32.sample_n(n_keep)
+    acc = float(s32.last_accept.float().mean())
+    assert 0.7 < acc < 0.995, acc
+    C64 = 128                                                                # fp64 CUDA-core evaluation: 8x fewer chains
+    s64 = bk.HMCDiag(bk.HierLogReg(X, y, dtype=torch.float64), eps, L, init=th0[:C64], seed=0)
+    s64.sample_n(n_burn, keep_draws=False)
+    d64, _ = s64.sample_n(n_keep)
+    assert abs(float(s64.last_accept.float().mean()) - acc) < 0.05
+
+    def moments(d):
+        e = bk.ess(d, draws_first=True).clamp(min=4.0, max=float(d.shape[0]))        # [chains, params]
+        x = d.double()
+        n_eff = e.sum(0)                                                                 # independent chains add up
+        mean, var = x.mean((0, 1)), x.var((0, 1))
+        return np_(mean), np_(var), np_(n_eff)
+
+    m1, v1, n1 = moments(d32)
+    m2, v2, n2 = moments(d64)
+    se_mean = np.sqrt(v1 / n1 + v2 / n2)
+    assert np.all(np.abs(m1 - m2) <= 4 * se_mean + 1e-6), np.max(np.abs(m1 - m2) / se_mean)
+    se_var = np.sqrt(2 * v1 ** 2 / n1 + 2 * v2 ** 2 / n2)
+    assert np.all(np.abs(v1 - v2) <= 4 * se_var + 1e-9), np.max(np.abs(v1 - v2) / se_var)
+
+
+def test_c5_full_size_diagnostics(bk):
+    """BASELINE configs[4] at FULL size inside the GPU suite: 8,192 chains x 10,000 draws x 100 params in the
+    samplers' [draws, chains, params] layout, consumed in place.  AR(1) series with known phi (test_iat.py:11-26):
+    closed-form IAT (1 + phi) / (1 - phi); R-hat -> 1; acf[0] = 1, acf[1] -> phi; and, on a subset of series,
+    ess / rhat / autocorr within 1e-9 of the oracle on the identical arrays."""
+    from oracle import diagnostics as od
+    N, Cn, P = 10000, 8192, 100
+    g = torch.Generator(device="cuda").manual_seed(0)
+    phi = torch.rand(Cn, P, device="cuda", generator=g) * 0.9
+    x = torch.empty(N, Cn, P, device="cuda")
+    cur = torch.randn(Cn, P, device="cuda", generator=g) / torch.sqrt(1 - phi * phi)
+    for t in range(N):
+        cur = phi * cur + torch.randn(Cn, P, device="cuda", generator=g)
+        x[t] = cur
+    S = Cn * P
+    e = bk.ess(x, draws_first=True)                                   # 819,200 series
+    rel = ((N / e) / ((1 + phi) / (1 - phi)) - 1).abs()
+    assert float(rel.median()) < 0.08
+    r = bk.rhat(x, draws_first=True)
+    assert float((r - 1).abs().max()) < 5e-3
+    # oracle on identical arrays (a subset the NumPy code finishes in seconds)
+    sub = np_(x[:, :3, :2]).astype(np.float64)                        # [N, 3, 2]
+    for c in range(3):
+        for p_ in range(2):
+            want = od.iat_ess_batch(sub[:, c, p_][None], "imse")[1][0]
+            assert abs(float(e[c, p_]) / want - 1) < 1e-9
+    sub_r = np_(x[:, :, 0]).astype(np.float64).T                      # all 8,192 chains of parameter 0
+    assert abs(float(r[0]) / od.rhat(list(sub_r)) - 1) < 1e-9
+    # all-lag autocorrelation: every series of 10 parameters = 81,920 series ([series, N] fp64 out = 6.5 GB)
+    xa = x[:, :, :10].permute(1, 2, 0).reshape(-1, N)
+    a = bk.autocorr(xa)
+    ph = phi[:, :10].reshape(-1).double()
+    assert a.shape == (81920, N)
+    assert float((a[:, 0] - 1).abs().max()) < 1e-9
+    assert float((a[:, 1] - ph).abs().median()) < 0.02
+    want = od.autocorr_batch(sub[:, 0, :2].T.copy())                  # chain 0, params 0 and 1 = series 0 and 1
+    np.testing.assert_allclose(np_(a[:2]), want, rtol=0, atol=1e-9)
+    del x, a, e
+
+
+def test_c4_smc_gpu_vs_reference_replicates(bk):
+    """The reference's one-move-per-temperature SMC is itself biased in high dimension, so
+    the fp32 device-RNG check is GPU vs reference AT IDENTICAL (M, T, scale) over replicates, not GPU vs the
+    analytic posterior: the replicate distribution of the posterior-mean estimate must agree within 4 standard
+    errors per dimension.  Reference replicates = the oracle restatement (bit-identical to the live reference on
+    every fixture) fed fresh NumPy streams."""
+    from oracle import samplers as osm
+    from oracle.models import GaussPriorLik
+    D, M, T, scale, R = 5, 400, 10, 0.3, 24
+    rng = np.random.default_rng(7)
+    mu = rng.normal(size=D)
+    om = GaussPriorLik(np.zeros(D), np.ones(D), mu, 4 * np.ones(D))
+    dm = bk.GaussPriorLik(np.zeros(D), np.ones(D), mu, 4 * np.ones(D))
+    ref_means, gpu_means, ref_vars, gpu_vars = [], [], [], []
+    for rep in range(R):
+        th0 = rng.normal(size=(M, D))
+        zs, au, ru = rng.standard_normal((T, M, D)), rng.random((T, M)), rng.random((T, M))
+        th, _ = osm.smc_tempered(om, th0, zs, au, ru, scale, T)                 # multinomial, like smc.py:64-75
+        ref_means.append(th.mean(0)); ref_vars.append(th.var(0))
+        smc = bk.TemperedLikelihoodSMC(dm, M, T, th0, bk.metropolis_kernel(scale), seed=1000 + rep)
+        smc.run()
+        g = np_(smc.thetas).astype(np.float64)
+        gpu_means.append(g.mean(0)); gpu_vars.append(g.var(0))
+    for a, b in ((np.array(ref_means), np.array(gpu_means)), (np.array(ref_vars), np.array(gpu_vars))):
+        se = np.sqrt(a.var(0, ddof=1) / R + b.var(0, ddof=1) / R)
+        assert np.all(np.abs(a.mean(0) - b.mean(0)) <= 4 * se), np.abs(a.mean(0) - b.mean(0)) / se
