@@ -67,8 +67,9 @@ def test_series_major_draws(bk, kind, n):
         e_series = bk.ess(ds.reshape(C * D, n)).reshape(C, D)   # contiguous series: streamed in place, no gather
         e_draws = bk.ess(d, draws_first=True)
         np.testing.assert_allclose(np_(e_series), np_(e_draws), rtol=1e-9)
-        ac = bk.autocorr(ds.reshape(C * D, n)[:5])
-        want = bk.autocorr(d[:, 0, :5].t().contiguous())
+        k = min(5, D)
+        ac = bk.autocorr(ds.reshape(C * D, n)[:k])
+        want = bk.autocorr(d[:, 0, :k].t().contiguous())
         np.testing.assert_allclose(np_(ac), np_(want), rtol=0, atol=1e-12)
 
 
