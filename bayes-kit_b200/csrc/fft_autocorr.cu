@@ -20,6 +20,8 @@
 //  * The first forward pass reads the series directly (demean, pack, zero-pad on the
 //    fly); the last inverse pass writes only the N wanted lags, scaled.
 // A CTA (256 threads, persistent) processes one pair at a time.
+#include <stdlib.h>
+
 #include "diag.h"
 
 namespace bk {
@@ -257,6 +259,252 @@ k_acf_fft(SeriesView v, int64_t S, FftPlan plan, const cplx* __restrict__ W, cpl
     }
 }
 
+// =====================================================================================
+// Shared-memory path: one REAL series per CTA, the whole transform on chip
+// =====================================================================================
+// The reference pads to S = 2^ceil(log2(2N-1)) (autocorr.py:26); any S >= 2N - 1 gives the same linear
+// correlation, so this path picks the smallest S = c 2^a (c in {1, 3, 5}) whose HALF-length complex
+// transform fits in shared memory: N = 10,000 -> S = 20,480, M = S / 2 = 10,240 complex doubles = 160 KB.
+//   z_n = d_2n + i d_2n+1 (even / odd samples packed), Z = DFT_M(z) in place (decimation in frequency,
+//   mixed radix: the odd factor first, then radix 16 / 8 / 4 / 2), natural -> digit-reversed;
+//   pointwise, for every pair (k, M - k):  X[k] = E[k] + w_S^k O[k]  (E, O = spectra of the even / odd
+//   samples),  P = |X|^2, and straight on to the packed spectrum of the (real, even) autocorrelation
+//   Z'[k] = (P[k] + P[M-k]) + i conj(w_S^k) (P[k] - P[M-k]);  r_0 = sum_k P[k] is reduced on the way;
+//   z' = IDFT_M(Z') (decimation in time, digit-reversed -> natural): acf_2n + i acf_2n+1 = z'_n / r_0.
+// The series is read twice (mean, then the packed load), the N lags are written once; nothing else touches
+// global memory except the twiddle tables (L2).  acf_k = r_k / r_0 equals autocorr.py:29-32's
+// ifft(|fft|^2).real / var / N because r_0 = N var.
+constexpr int RF_THREADS = 512;
+constexpr int RF_MAX_M_CONST = 11264;     // (M + M / 8) complex doubles = 198 KB of shared memory for the skewed M-point line
+
+template <int R, bool INV>
+__device__ __forceinline__ void dft_small(cplx (&a)[R]) {
+    if constexpr (R == 3) {
+        const double h = 0.86602540378443864676;                  // sqrt(3) / 2
+        const cplx t1 = cadd(a[1], a[2]);
+        const cplx t2 = cplx{a[0].x - 0.5 * t1.x, a[0].y - 0.5 * t1.y};
+        const cplx t3 = cplx{h * (a[1].x - a[2].x), h * (a[1].y - a[2].y)};
+        a[0] = cadd(a[0], t1);
+        const cplx m = cplx{t2.x + t3.y, t2.y - t3.x}, p = cplx{t2.x - t3.y, t2.y + t3.x};   // t2 -+ i t3
+        a[1] = INV ? p : m;
+        a[2] = INV ? m : p;
+    } else if constexpr (R == 5) {
+        const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;      // cos(2 pi/5), cos(4 pi/5)
+        const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;       // sin(2 pi/5), sin(4 pi/5)
+        const cplx t1 = cadd(a[1], a[4]), t2 = cadd(a[2], a[3]), t3 = csub(a[1], a[4]), t4 = csub(a[2], a[3]);
+        const cplx m1 = cplx{a[0].x + c1 * t1.x + c2 * t2.x, a[0].y + c1 * t1.y + c2 * t2.y};
+        const cplx m2 = cplx{a[0].x + c2 * t1.x + c1 * t2.x, a[0].y + c2 * t1.y + c1 * t2.y};
+        const cplx n1 = cplx{s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y};
+        const cplx n2 = cplx{s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y};
+        a[0] = cadd(a[0], cadd(t1, t2));
+        const cplx y1 = cplx{m1.x + n1.y, m1.y - n1.x}, y4 = cplx{m1.x - n1.y, m1.y + n1.x};   // m1 -+ i n1
+        const cplx y2 = cplx{m2.x + n2.y, m2.y - n2.x}, y3 = cplx{m2.x - n2.y, m2.y + n2.x};
+        a[1] = INV ? y4 : y1; a[4] = INV ? y1 : y4;
+        a[2] = INV ? y3 : y2; a[3] = INV ? y2 : y3;
+    } else {
+        dft_reg<R, INV>(a);
+    }
+}
+template <int R>
+__host__ __device__ constexpr int out_slot(int k) { return (R == 3 || R == 5) ? k : bitrev<R>(k); }
+
+struct RfftPlan {
+    int M, n_pass;
+    int radix[6];       // forward pass i has radix radix[i]; block length after pass i: m[i]
+    int m[6];
+};
+
+// Twiddles w_M^e = exp(-2 pi i e / M) from two small shared-memory tables, w^e = A[e >> 6] * B[e & 63]: one
+// complex multiply per twiddle and NO dependency between the R - 1 twiddles of a butterfly (a running product
+// w^k = w^(k-1) w is a serial chain of fp64 multiplies -- with 8 warps per SM the kernel was latency-bound on it).
+constexpr int RF_TW_LO = 64, RF_TW_HI_MAX = RF_MAX_M_CONST / RF_TW_LO + 1;
+struct RfTw {
+    const cplx* hi;   // [ceil(M / 64)]  w^(64 j)
+    const cplx* lo;   // [64]            w^j
+    __device__ __forceinline__ cplx at(int e, bool inv) const {
+        cplx w = cmul(hi[e >> 6], lo[e & 63]);
+        if (inv) w.y = -w.y;
+        return w;
+    }
+};
+
+// one in-place radix-R pass over the M-point line in shared memory; block length n = R m (see radix_pass)
+template <int R, bool INV, class Load, class Store>
+__device__ __forceinline__ void rf_pass(int M, int m, const RfTw& tw, Load ld, Store st) {
+    const int cnt = M / R, n = R * m, tw_stride = M / n;
+    const int log2m = 31 - __clz(m);            // m is a power of two in every pass (the odd factor goes first)
+    for (int t = threadIdx.x; t < cnt; t += RF_THREADS) {
+        const int p = t & (m - 1), base = (t >> log2m) * n + p;
+        const int q = p * tw_stride;            // w_n^(p k) = w_M^(k q), k q < M for every k < R
+        cplx a[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            a[j] = ld(base + j * m);
+            if (INV && j > 0) a[j] = cmul(a[j], tw.at(j * q, true));
+        }
+        dft_small<R, INV>(a);
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            cplx v = a[out_slot<R>(k)];
+            if (!INV && k > 0) v = cmul(v, tw.at(k * q, false));
+            st(base + k * m, v);
+        }
+    }
+    __syncthreads();
+}
+template <bool INV, class Load, class Store>
+__device__ __forceinline__ void rf_pass_r(int R, int M, int m, const RfTw& tw, Load ld, Store st) {
+    switch (R) {
+        case 16: rf_pass<16, INV>(M, m, tw, ld, st); break;
+        case 8: rf_pass<8, INV>(M, m, tw, ld, st); break;
+        case 5: rf_pass<5, INV>(M, m, tw, ld, st); break;
+        case 4: rf_pass<4, INV>(M, m, tw, ld, st); break;
+        case 3: rf_pass<3, INV>(M, m, tw, ld, st); break;
+        default: rf_pass<2, INV>(M, m, tw, ld, st); break;
+    }
+}
+// position of frequency k after the forward passes (mixed-radix digit reversal)
+__device__ __forceinline__ int rf_pos(const RfftPlan& pl, int k) {
+    int i = 0;
+    for (int ps = 0; ps < pl.n_pass; ++ps) {
+        int d;
+        switch (pl.radix[ps]) {          // constant divisors: shifts / multiply-shift instead of a runtime division
+            case 16: d = k & 15; k >>= 4; break;
+            case 8: d = k & 7; k >>= 3; break;
+            case 4: d = k & 3; k >>= 2; break;
+            case 2: d = k & 1; k >>= 1; break;
+            case 5: d = k % 5; k /= 5; break;
+            default: d = k % 3; k /= 3; break;
+        }
+        i += d * pl.m[ps];
+    }
+    return i;
+}
+
+__global__ void __launch_bounds__(RF_THREADS, 1)
+k_acf_rfft(SeriesView v, RfftPlan plan, const cplx* __restrict__ WM, const cplx* __restrict__ WS, double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char rf_smem[];
+    cplx* buf = reinterpret_cast<cplx*>(rf_smem);          // [M]
+    __shared__ double red[33];
+    __shared__ cplx tw_hi[RF_TW_HI_MAX], tw_lo[RF_TW_LO];
+    const int M = plan.M;
+    for (int j = threadIdx.x; j * RF_TW_LO < M; j += RF_THREADS) tw_hi[j] = WM[j * RF_TW_LO];
+    for (int j = threadIdx.x; j < RF_TW_LO; j += RF_THREADS) tw_lo[j] = WM[j < M ? j : 0];
+    __syncthreads();
+    const RfTw WMt{tw_hi, tw_lo};
+    const int64_t N = v.N;
+    // element i lives at i + i / 8: the butterflies of the late passes walk the line with strides of 8 and 128
+    // elements (16 B each) -- unskewed that is a 32-way / 4-way bank conflict, skewed every access pattern of the
+    // transform costs the minimum of four wavefronts per 512-byte warp request
+    auto SK = [](int i) { return i + (i >> 3); };
+    auto ld_buf = [&](int i) { return buf[SK(i)]; };
+    auto st_buf = [&](int i, cplx val) { buf[SK(i)] = val; };
+    for (int64_t s = blockIdx.x; s < v.n_series; s += gridDim.x) {
+        double l1 = 0;
+        for (int64_t t = threadIdx.x; t < N; t += RF_THREADS) l1 += v.at(s, t);
+        const double mean = block_sum(l1, red) / (double)N;
+        // ---- forward: packed load (even + i odd, demeaned, zero padded) fused into the first pass ----
+        for (int ps = 0; ps < plan.n_pass; ++ps) {
+            if (ps == 0) {
+                auto ld = [&](int i) {
+                    const int64_t e = 2 * (int64_t)i;
+                    return cplx{e < N ? v.at(s, e) - mean : 0.0, e + 1 < N ? v.at(s, e + 1) - mean : 0.0};
+                };
+                rf_pass_r<false>(plan.radix[ps], M, plan.m[ps], WMt, ld, st_buf);
+            } else {
+                rf_pass_r<false>(plan.radix[ps], M, plan.m[ps], WMt, ld_buf, st_buf);
+            }
+        }
+        // ---- pointwise: power spectrum of the real series -> packed spectrum of its autocorrelation ----
+        double r0 = 0;
+        for (int k = threadIdx.x; k <= M / 2; k += RF_THREADS) {
+            const int k2 = (M - k) % M;                    // partner (k = 0 pairs with itself and carries X[M])
+            const int i = SK(rf_pos(plan, k)), i2 = SK(rf_pos(plan, k2));
+            const cplx a = buf[i], b = buf[i2];
+            if (k == 0) {
+                const double x0 = 2.0 * (a.x + a.y), xm = 2.0 * (a.x - a.y);   // X[0] = E + O, X[M] = E - O (real; x2 like the k > 0 terms)
+                const double p0 = x0 * x0, pm = xm * xm;
+                r0 += p0 + pm;
+                buf[i] = cplx{p0 + pm, p0 - pm};
+            } else {
+                // E = (Z[k] + conj Z[M-k]) / 2, O = (Z[k] - conj Z[M-k]) / 2i  (the factors 1/2 cancel in acf = r / r0)
+                const cplx E = cplx{a.x + b.x, a.y - b.y}, O = cplx{a.y + b.y, b.x - a.x};
+                const cplx w = WS[k];                                   // exp(-2 pi i k / S)
+                const cplx wo = cmul(w, O);
+                const cplx Xk = cadd(E, wo);                            // X[k]
+                const cplx Xm = cplx{E.x - wo.x, -(E.y - wo.y)};        // X[M-k] = conj(E - w O)
+                const double pk = fma(Xk.x, Xk.x, Xk.y * Xk.y), pm = fma(Xm.x, Xm.x, Xm.y * Xm.y);
+                r0 += (k == k2) ? 2.0 * pk : 2.0 * (pk + pm);
+                // Z'[k] = (P[k] + P[M-k]) + i conj(w^k) (P[k] - P[M-k]);  Z'[M-k] = (P[k] + P[M-k]) + i w^k (P[k] - P[M-k]) ... sign below
+                const double sm = pk + pm, df = pk - pm;
+                // i * conj(w) * df = i (w.x - i w.y) df = (w.y df, w.x df)
+                buf[i] = cplx{sm + w.y * df, w.x * df};
+                if (k != k2) {
+                    // at M-k: exp(+2 pi i (M-k) / S) = -conj(exp(+2 pi i k / S)) = -w  ->  i * (-w) * (P[M-k] - P[k]) = i w df
+                    buf[i2] = cplx{sm - w.y * df, w.x * df};
+                }
+            }
+        }
+        r0 = block_sum(r0, red);
+        __syncthreads();
+        // ---- inverse: digit-reversed -> natural; the last pass writes acf_2n, acf_2n+1 = z'_n / r0 ----
+        const double sc = 1.0 / r0;
+        for (int ps = plan.n_pass - 1; ps >= 0; --ps) {
+            if (ps == 0) {
+                auto st_out = [&](int i, cplx val) {
+                    const int64_t e = 2 * (int64_t)i;
+                    if (e < N) out[s * N + e] = val.x * sc;
+                    if (e + 1 < N) out[s * N + e + 1] = val.y * sc;
+                };
+                rf_pass_r<true>(plan.radix[ps], M, plan.m[ps], WMt, ld_buf, st_out);
+            } else {
+                rf_pass_r<true>(plan.radix[ps], M, plan.m[ps], WMt, ld_buf, st_buf);
+            }
+        }
+    }
+}
+
+// WM[j] = exp(-2 pi i j / M) (j < M), WS[k] = exp(-2 pi i k / (2 M)) (k <= M / 2)
+__global__ void k_rfft_twiddles(cplx* __restrict__ WM, cplx* __restrict__ WS, int M) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    double sn, cs;
+    if (j < M) {
+        sincospi(-2.0 * (double)j / (double)M, &sn, &cs);
+        WM[j] = cplx{cs, sn};
+    }
+    if (j <= M / 2) {
+        sincospi(-(double)j / (double)M, &sn, &cs);
+        WS[j] = cplx{cs, sn};
+    }
+}
+
+constexpr int RF_MAX_M = RF_MAX_M_CONST;
+// smallest S = c 2^a >= 2N - 1 (c in {1, 3, 5}, S even) whose half-length transform fits on chip; 0: none
+static int64_t rfft_size(int64_t N) {
+    int64_t best = 0;
+    for (int c : {1, 3, 5})
+        for (int64_t S = 2 * c; S / 2 <= RF_MAX_M; S *= 2)
+            if (S >= 2 * N - 1) { if (!best || S < best) best = S; break; }
+    return best;
+}
+static RfftPlan rfft_plan(int M) {
+    RfftPlan p;
+    memset(&p, 0, sizeof(p));
+    p.M = M;
+    int rest = M;
+    auto push = [&](int r) { rest /= r; p.radix[p.n_pass] = r; p.m[p.n_pass] = rest; ++p.n_pass; };
+    if (rest % 5 == 0) push(5);
+    else if (rest % 3 == 0) push(3);
+    while (rest % 16 == 0 && rest > 16) push(16);
+    while (rest > 1) {
+        if (rest % 16 == 0) push(16);
+        else if (rest % 8 == 0) push(8);
+        else if (rest % 4 == 0) push(4);
+        else push(2);
+    }
+    return p;
+}
+
 static int64_t fft_size(int64_t N) {
     int64_t S = 1;
     while (S < 2 * N - 1) S <<= 1;   // 2 ** ceil(log2(2N - 1))
@@ -281,12 +529,43 @@ static FftPlan fft_plan(int64_t S) {
     return p;
 }
 
+static bool use_rfft(int64_t N) {
+    const char* e = getenv("BK_ACF_RFFT");      // diagnostic: BK_ACF_RFFT=0 forces the global-scratch transform
+    return !(e && e[0] == '0') && rfft_size(N) > 0;
+}
+
 size_t acf_fft_ws_bytes(int64_t n_series, int64_t N) {
+    if (use_rfft(N)) {
+        const int64_t M = rfft_size(N) / 2;
+        return align_up((size_t)M * sizeof(cplx), 256) + align_up((size_t)(M / 2 + 1) * sizeof(cplx), 256) + 512;
+    }
     const int64_t S = fft_size(N);
     return align_up((size_t)S * sizeof(cplx), 256) + (size_t)fft_blocks(n_series) * S * sizeof(cplx) + 512;
 }
 
 int acf_fft_launch(const SeriesView& v, double* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (use_rfft(v.N)) {
+        const int M = (int)(rfft_size(v.N) / 2);
+        Arena ar(ws, ws_bytes);
+        cplx* WM = ar.take<cplx>((size_t)M);
+        cplx* WS = ar.take<cplx>((size_t)(M / 2 + 1));
+        if (!ar.ok()) {
+            set_error("bk_autocorr: workspace too small (need %zu bytes, got %zu)", ar.off, ws_bytes);
+            return BK_E_WORKSPACE;
+        }
+        k_rfft_twiddles<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(WM, WS, M);
+        BK_LAUNCH_CHECK();
+        const size_t smem = (size_t)(M + M / 8 + 1) * sizeof(cplx);
+        BK_CUDA(cudaFuncSetAttribute(k_acf_rfft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+        const int64_t nb = v.n_series < (int64_t)sms * per_sm ? v.n_series : (int64_t)sms * per_sm;
+        k_acf_rfft<<<(unsigned)nb, RF_THREADS, smem, st>>>(v, rfft_plan(M), WM, WS, out);
+        BK_LAUNCH_CHECK();
+        return BK_OK;
+    }
     const int64_t S = fft_size(v.N);
     if (S > ((int64_t)1 << 20)) {
         set_error("bk_autocorr: series of %lld draws need a transform of %lld points (limit 2^20)", (long long)v.N,

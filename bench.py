@@ -205,7 +205,7 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return run_reference_arm(args)
-    for v in ("BK_TC_DEBUG", "BK_DISABLE_TC", "BK_FORCE_GENERIC", "BK_HLR_DEBUG", "BK_ESS", "BK_ACF", "BK_LIB", "BK_TC_FUSE", "BK_TC_PAIR", "BK_SEP_WIDE", "BK_SMC_LAYOUT", "BK_SMC_OCC"):   # diagnostic switches of the library
+    for v in ("BK_TC_DEBUG", "BK_DISABLE_TC", "BK_FORCE_GENERIC", "BK_HLR_DEBUG", "BK_ESS", "BK_ACF", "BK_LIB", "BK_TC_FUSE", "BK_TC_PAIR", "BK_SEP_WIDE", "BK_SMC_LAYOUT", "BK_SMC_OCC", "BK_ACF_RFFT"):   # diagnostic switches of the library
         if os.environ.get(v, "0") not in ("", "0"):
             raise SystemExit(f"{v} is set: refusing to benchmark a diagnostic configuration")
 
