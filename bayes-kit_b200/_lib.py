@@ -76,6 +76,7 @@ _SIGNATURES = {
     "bk_model_log_density_gradient": (C.c_int, [u64, vp, i64, vp, vp, vp, sz, vp]),
     "bk_model_log_density_gradient_fast": (C.c_int, [u64, vp, i64, vp, vp, vp, sz, vp]),
     "bk_model_log_prior_likelihood": (C.c_int, [u64, vp, i64, vp, vp, vp]),
+    "bk_init_normal": (C.c_int, [vp, i64, i64, i32, u64, u64, C.c_uint32, vp]),
     "bk_hmc_diag_workspace_bytes": (sz, [u64, i64]),
     "bk_hmc_diag_sample": (C.c_int, [u64, vp, vp, vp, C.POINTER(i32), i64, f64, i32, vp, i64,
                                      C.POINTER(Rng), C.POINTER(DrawOut), vp, sz, vp]),

@@ -40,10 +40,8 @@ class ChainSampler:
         if _is_empty_init(init):
             n = 1 if chains is None else int(chains)
             self._single = chains is None
-            # theta0 ~ N(0, I) like rng.normal(size=dim) (hmc.py:27)
-            g = torch.Generator(device=self.device)
-            g.manual_seed((self._seed * 0x9E3779B97F4A7C15 + self._chain_offset) % (2**63))
-            th = torch.randn(n, self._dim, generator=g, device=self.device, dtype=self.dtype)
+            # theta0 ~ N(0, I) like rng.normal(size=dim) (hmc.py:27): device Philox keyed by the GLOBAL chain id
+            th = self._philox_normal(n, 0xFFFFFFFF)
         else:
             th = to_dev(init, self.dtype, self.device)
             self._single = th.dim() == 1
@@ -61,6 +59,14 @@ class ChainSampler:
         self._grad = None
         self._cache_valid = L.i32(0)
         self.last_accept = None
+
+    def _philox_normal(self, n: int, draw: int) -> torch.Tensor:
+        """[n, D] standard normals for global chains chain_offset .. chain_offset + n (shard invariant)."""
+        out = torch.empty(n, self._dim, dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(L.lib().bk_init_normal(out.data_ptr(), n, self._dim, L.BK_F32 if self.dtype == torch.float32 else L.BK_F64,
+                                           self._seed & 0xFFFFFFFFFFFFFFFF, self._chain_offset, draw, stream_ptr(self.device)))
+        return out
 
     # ---- reference surface ---------------------------------------------------------
     def __iter__(self) -> Iterator[DrawAndLogP]:

@@ -194,7 +194,39 @@ int finish_extras(const Model& m, const bk_draw_out& o, int64_t C, int64_t n, vo
 
 }  // namespace
 
+namespace {
+// out[c, :] = standard normals of global chain (chain_offset + c), Philox draw index `draw`, element blocks of 4 --
+// the same (block, chain, draw) coordinates the samplers use, so initial states do not depend on the sharding
+template <typename T>
+__global__ void k_init_normal(T* __restrict__ out, int64_t C, int D, uint64_t seed, uint64_t chain_offset, uint32_t draw) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nb = (D + 3) / 4;
+    if (i >= C * nb) return;
+    const int64_t c = i / nb;
+    const int b = (int)(i % nb);
+    T z[4];
+    philox_normal4<T>(seed, (uint32_t)b, (uint32_t)(chain_offset + (uint64_t)c), draw, z);
+    for (int k = 0; k < 4; ++k)
+        if (4 * b + k < D) out[c * (int64_t)D + 4 * b + k] = z[k];
+}
+}  // namespace
+
 extern "C" {
+
+int bk_init_normal(void* out, int64_t C, int64_t D, int32_t dtype, uint64_t seed, uint64_t chain_offset, uint32_t draw,
+                   void* stream) {
+    BK_CHECK_ARG(out && C >= 0 && D >= 1, "bk_init_normal: bad argument");
+    if (C == 0) return BK_OK;
+    const int64_t n = C * ((D + 3) / 4);
+    if (dtype == BK_F64)
+        k_init_normal<double><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((double*)out, C, (int)D, seed,
+                                                                                           chain_offset, draw);
+    else
+        k_init_normal<float><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((float*)out, C, (int)D, seed,
+                                                                                          chain_offset, draw);
+    BK_LAUNCH_CHECK();
+    return BK_OK;
+}
 
 size_t bk_hmc_diag_workspace_bytes(uint64_t h, int64_t C) { return sampler_ws(h, C); }
 size_t bk_mala_workspace_bytes(uint64_t h, int64_t C) { return sampler_ws(h, C); }

@@ -132,10 +132,11 @@ struct Philox {
 // tags separate the independent streams of one (chain, draw)
 enum : uint32_t { TAG_NORMAL = 0, TAG_NORMAL_HI = 1, TAG_UNIFORM = 2, TAG_RESAMPLE = 3 };
 
-// uniforms strictly inside (0,1): midpoints of the 2^-24 / 2^-53 grid
-__host__ __device__ __forceinline__ float u01(uint32_t x) { return ((x >> 8) + 0.5f) * 5.9604644775390625e-8f; }
+// uniforms strictly inside (0,1): midpoints of the 2^-23 / 2^-52 grid.  k + 0.5 must be REPRESENTABLE (24 / 53
+// significant bits), otherwise round-to-even turns the top of the range into exactly 1.0: 23 / 52 random bits.
+__host__ __device__ __forceinline__ float u01(uint32_t x) { return ((x >> 9) + 0.5f) * 1.1920928955078125e-7f; }
 __host__ __device__ __forceinline__ double u01d(uint32_t hi, uint32_t lo) {
-    return (((double)(hi >> 5)) * 67108864.0 + (double)(lo >> 6) + 0.5) * 1.1102230246251565e-16;
+    return (((double)(hi >> 6)) * 67108864.0 + (double)(lo >> 6) + 0.5) * 2.220446049250313e-16;
 }
 
 // 4 standard normals for element block `block` of (chain, draw)

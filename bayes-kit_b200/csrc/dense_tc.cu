@@ -1189,7 +1189,7 @@ int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* 
     }
     int rc;
     if (!cache_valid || !*cache_valid) {
-        rc = model_eval(m, theta, C, lp, grad, ews, ebytes, st);   // exact fp32 CUDA-core evaluation
+        rc = model_eval(m, theta, C, lp, grad, ews, ebytes, st);   // same functions as the trajectory ends: 3-pass split tensor-core gradient, lp = 0.5 (q - mu).g (model.cu eval_t)
         if (rc) return rc;
         if (cache_valid) *cache_valid = 1;
     }

@@ -49,10 +49,8 @@ class DrGhmcDiag(ChainSampler):
             if m.numel() != self._dim:
                 raise ValueError(f"metric_diag must have {self._dim} entries")
             self._metric = m
-        # rho0 ~ N(0, I) (drghmc.py:77)
-        g = torch.Generator(device=self.device)
-        g.manual_seed((self._seed * 0xD1B54A32D192ED03 + 1 + self._chain_offset) % (2**63))
-        self._rho = torch.randn(self._C, self._dim, generator=g, device=self.device, dtype=self.dtype)
+        # rho0 ~ N(0, I) (drghmc.py:77): device Philox keyed by the global chain id, like theta0
+        self._rho = self._philox_normal(self._C, 0xFFFFFFFE)
         self._sizes = (C.c_double * int(max_proposals))(*[float(s) for s in leapfrog_step_sizes])
         self._counts = (C.c_int32 * int(max_proposals))(*[int(c) for c in leapfrog_step_counts])
         self.last_n_uniform = None

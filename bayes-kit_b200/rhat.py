@@ -69,8 +69,9 @@ def rhat(chains, device="cuda", draws_first=False, group=None, reduce_fn=None):
 
     ``chains``: the reference's list of 1-D chains (ragged allowed, returns a
     float), a ``[chains, draws]`` array (float / 0-dim tensor) or
-    ``[chains, draws, params]`` (tensor [params]).  With torch.distributed
-    initialised and ``group`` given (or the default group), ``chains`` is this
+    ``[chains, draws, params]`` (tensor [params]).  With ``group`` given
+    (``torch.distributed.group.WORLD`` for all ranks; the call is then COLLECTIVE over that
+    group -- without ``group`` it is always local, also under torchrun), ``chains`` is this
     rank's shard of chains (all of one length) and the only communication is an
     all-reduce of a [params, 4] table of moment sums (``_rhat_allreduce``).  Raises ValueError for < 2 chains or a chain with < 2
     draws (rhat.py:157-162)."""
@@ -78,7 +79,7 @@ def rhat(chains, device="cuda", draws_first=False, group=None, reduce_fn=None):
     ragged = (isinstance(chains, (list, tuple)) and len(chains) > 0
               and len({len(c) for c in chains}) > 1)
     if isinstance(chains, (list, tuple)):
-        if len(chains) < 2 and D_.rank_world(group)[1] == 1:
+        if len(chains) < 2 and (group is None or D_.rank_world(group)[1] == 1):
             raise ValueError(f"rhat requires len(chains) >= 2, but len(chains) = {len(chains)}")
         if not all(len(c) >= 2 for c in chains):
             raise ValueError("rhat requires len(chain) >= 2 for every chain in chains")
@@ -96,7 +97,7 @@ def rhat(chains, device="cuda", draws_first=False, group=None, reduce_fn=None):
     scalar = mean.dim() <= 1
     mean = mean.reshape(mean.shape[0] if mean.dim() else 1, -1)
     var = var.reshape(mean.shape)
-    if D_.rank_world(group)[1] > 1 or reduce_fn is not None:
+    if (group is not None and D_.rank_world(group)[1] > 1) or reduce_fn is not None:
         out = _rhat_allreduce(mean, var, N, group, reduce_fn)
     else:
         out = _rhat_from(mean, var, None, N)

@@ -231,6 +231,12 @@ def main():
     # theta0 ~ N(0, I) per chain (the reference's default init, hmc.py:27); global chain ids
     sampler = bk.HMCDiag(model, EPS, L, chains=C, seed=0, chain_offset=rank * C)
 
+    t_start = time.perf_counter()
+
+    def stage(msg):
+        if os.environ.get("BENCH_VERBOSE", "0") == "1":
+            print(f"[bench rank {rank} +{time.perf_counter() - t_start:7.2f}s] {msg}", file=sys.stderr, flush=True)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -243,6 +249,7 @@ def main():
         return float(t)
 
     # ---- device-resident throughput ------------------------------------------------
+    stage("model + sampler ready")
     for _ in range(args.warmup):
         sampler.sample_n(n)
     barrier()
@@ -269,6 +276,7 @@ def main():
     clk = clocks.stop() if rank == 0 else None
     ms_max = rank_max(ms)
     value = world * C * n * args.steps / (ms_max * 1e-3)
+    stage(f"device-resident done: {ms:.1f} ms")
 
     # ---- end to end through the public API with host buffers --------------------------
     # One step = the call a user of the reference makes for n draws of every chain, host arrays in and out
@@ -284,9 +292,11 @@ def main():
         # rows are uploaded before that chunk's draws are written back, so the aliasing is safe)
         sampler.sample_host_n(n, host_draws[n - 1], out=(host_draws, host_lp), chunk_chains=args.e2e_chunk or None)
 
+    stage("pinned buffers ready")
     for _ in range(2):
         e2e_step()
     barrier()
+    stage("e2e warm-up done")
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
@@ -304,6 +314,7 @@ def main():
     barrier()
     floor_s = rank_max((time.perf_counter() - t0) / 2)
     del dsrc
+    stage(f"e2e done: {e2e_s:.2f} s, floor {floor_s:.3f} s")
 
     # ---- secondary workloads (all ranks take part in the sharded ones) ------------------
     peaks = {}
@@ -325,19 +336,25 @@ def main():
                          ("c3", lambda: legs.leg_c3(rank, world, peak_tf))):
             if name == "c4_weak" and world == 1:
                 continue
+            stage(f"leg {name} ...")
             try:
                 secondary[name] = fn()
             except Exception as e:      # a failed leg must not lose the headline
                 secondary[name] = {"error": repr(e)}
+                stage(f"leg {name} FAILED: {e!r}")
             torch.cuda.empty_cache()
+        stage("sharded legs done")
         if rank == 0:
             for name, fn in (("c1", lambda: legs.leg_c1(peak_bw)), ("c2_mala", lambda: legs.leg_c2_mala(peak_bw, peak_tf)),
                              ("c5", lambda: legs.leg_c5(peak_bw))):
+                stage(f"leg {name} ...")
                 try:
                     secondary[name] = fn()
                 except Exception as e:
                     secondary[name] = {"error": repr(e)}
+                    stage(f"leg {name} FAILED: {e!r}")
                 torch.cuda.empty_cache()
+            stage("rank-0 legs done")
 
     if rank != 0:
         if world > 1:

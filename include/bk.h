@@ -152,6 +152,13 @@ BK_API int bk_model_log_density_gradient_fast(uint64_t handle, const void* theta
 BK_API int bk_model_log_prior_likelihood(uint64_t handle, const void* theta, int64_t C,
                                   void* log_prior_out, void* log_lik_out, void* stream);
 
+/* Initial states theta0 ~ N(0, I) (hmc.py:24-28, mala.py:26-30, metropolis.py:94-98; DrGhmcDiag's rho0,
+ * drghmc.py:77): out [C, D] filled with device-Philox standard normals keyed by the GLOBAL chain id
+ * (chain_offset + c) and draw index `draw` (the samplers reserve 0xFFFFFFFF for theta0 and 0xFFFFFFFE for
+ * rho0), so the initial state of a chain does not depend on how the chains are sharded over GPUs. */
+BK_API int bk_init_normal(void* out, int64_t C, int64_t D, int32_t dtype, uint64_t seed, uint64_t chain_offset,
+                   uint32_t draw, void* stream);
+
 /* ---- HMCDiag (hmc.py:9-63): n_draws calls of sample() for C chains ------- */
 BK_API size_t bk_hmc_diag_workspace_bytes(uint64_t handle, int64_t C);
 /* theta [C,D] in/out.  lp_cache [C] / grad_cache [C,D] hold log p and its

@@ -142,6 +142,17 @@ def test_shard_invariance(bk):
     full = bk.HMCDiag(model, 0.2, 5, init=init, seed=9).sample_n(10)[0]
     part = bk.HMCDiag(model, 0.2, 5, init=init[40:64], seed=9, chain_offset=40).sample_n(10)[0]
     assert torch.equal(full[:, 40:64], part)
+    # init=None: theta0 (and DrGhmcDiag's rho0) come from device Philox keyed by the global chain id too
+    f = bk.HMCDiag(model, 0.2, 5, chains=64, seed=9)
+    p = bk.HMCDiag(model, 0.2, 5, chains=24, seed=9, chain_offset=40)
+    assert torch.equal(f.theta[40:64], p.theta)
+    assert torch.equal(f.sample_n(3)[0][:, 40:64], p.sample_n(3)[0])
+    assert abs(float(f.theta.mean())) < 0.2 and abs(float(f.theta.std()) - 1) < 0.1
+    fd = bk.DrGhmcDiag(model, 2, [0.4, 0.2], [3, 6], 0.5, chains=64, seed=9)
+    pd = bk.DrGhmcDiag(model, 2, [0.4, 0.2], [3, 6], 0.5, chains=24, seed=9, chain_offset=40)
+    assert torch.equal(fd.rho[40:64], pd.rho) and torch.equal(fd.theta[40:64], pd.theta)
+    assert not torch.equal(fd.rho, fd.theta)
+    assert torch.equal(fd.sample_n(4)[0][:, 40:64], pd.sample_n(4)[0])
 
 
 def test_smc_posterior(bk):  # test_tempered_smc.py:8-30 (Gaussian analogue)
