@@ -34,6 +34,6 @@ elif w in ("ess", "acf"):
     if w == "ess":
         bk.ess(xs); bk.ess(xs)
     else:
-        bk.autocorr(xs[:512]); bk.autocorr(xs[:512])
+        bk.autocorr(xs); bk.autocorr(xs)
 torch.cuda.synchronize()
 print("done")
