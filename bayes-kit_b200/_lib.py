@@ -106,6 +106,8 @@ _SIGNATURES = {
     "bk_smc_shard_move": (C.c_int, [u64, C.POINTER(SmcShard), vp, i32, i32, C.POINTER(SmcKernel), C.POINTER(Rng), i32,
                                     vp, vp, sz, vp]),
     "bk_smc_shard_resample": (C.c_int, [C.POINTER(SmcShard), i32, i32, vp, C.POINTER(Rng), f64, i32, vp, vp, sz, vp]),
+    "bk_smc_shard_run": (C.c_int, [u64, C.POINTER(SmcShard), vp, i32, i32, i32, C.POINTER(SmcKernel), C.POINTER(Rng), i32, f64,
+                                   vp, vp, vp, sz, vp]),
     "bk_smc_shard_gather": (C.c_int, [C.POINTER(SmcShard), i64, i32, vp, vp]),
     "bk_rank_normalize_workspace_bytes": (sz, [i64, i32]),
     "bk_rank_normalize": (C.c_int, [vp, i32, C.POINTER(SeriesLayout), vp, vp, vp, sz, vp]),

@@ -1380,6 +1380,33 @@ int bk_smc_shard_resample(const bk_smc_shard* sh, int32_t dtype, int32_t mode, c
     return BK_OK;
 }
 
+int bk_smc_shard_run(uint64_t handle, const bk_smc_shard* sh, const void* src_local, int32_t n_from, int32_t n_to,
+                     int32_t T, const bk_smc_kernel* kernel, const bk_rng* rng, int32_t mode, double ess_threshold,
+                     double* stats_out, int32_t* accept_out, void* ws, size_t ws_bytes, void* stream) {
+    BK_CHECK_ARG(sh && rng && kernel, "bk_smc_shard_run: null argument");
+    BK_CHECK_ARG(rng->mode == BK_RNG_PHILOX, "bk_smc_shard_run: device Philox only (injected streams go step by step)");
+    BK_CHECK_ARG(n_from >= 1 && n_from <= n_to && n_to <= T, "bk_smc_shard_run: need 1 <= n_from <= n_to <= T");
+    const Model* m = get_model(handle);
+    if (!m) return BK_E_HANDLE;
+    bk_smc_shard s = *sh;
+    for (int32_t n = n_from; n <= n_to; ++n) {
+        bk_rng r = *rng;
+        r.draw_offset = (uint64_t)n;
+        const int accumulate = (ess_threshold > 0 && s.epoch > 1) ? 1 : 0;
+        int rc = bk_smc_shard_move(handle, &s, n == n_from ? src_local : nullptr, n, T, kernel, &r, accumulate,
+                                   n == n_to ? accept_out : nullptr, ws, ws_bytes, stream);
+        if (rc) return rc;
+        bk_rng rr = *rng;
+        rr.draw_offset = (uint64_t)n;
+        rr.chain_offset = 0;
+        rc = bk_smc_shard_resample(&s, m->d.dtype, mode, nullptr, &rr, ess_threshold, 0,
+                                   stats_out ? stats_out + 4 * (n - n_from) : nullptr, ws, ws_bytes, stream);
+        if (rc) return rc;
+        s.epoch += 1;
+    }
+    return BK_OK;
+}
+
 int bk_smc_shard_gather(const bk_smc_shard* sh, int64_t D, int32_t dtype, void* out, void* stream) {
     ShardGeom g;
     if (int rc = make_geom(sh, &g)) return rc;

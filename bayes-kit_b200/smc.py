@@ -216,9 +216,35 @@ class TemperedLikelihoodSMC:
         return iter(self.thetas)
 
     def run(self) -> None:
-        for n in range(1, self.N + 1):
-            self.transition(n)
+        """All N temperatures (smc.py:39-41), enqueued by ONE library call: three launches per temperature back to
+        back, no Python between the steps."""
+        self.run_steps(1, self.N)
         self._check()
+
+    def run_steps(self, n_from: int, n_to: int) -> None:
+        """Temperatures n_from..n_to in one library call (device Philox; injected streams go through transition())."""
+        lib = L.lib()
+        n_from, n_to = int(n_from), int(n_to)
+        if n_to < n_from:
+            return
+        Ml = self._hi - self._lo
+        k0 = len(self._steps_taken)
+        if k0 + (n_to - n_from + 1) > self._stats.shape[0]:
+            self._stats = torch.cat([self._stats, torch.zeros(n_to - n_from + 1, 4, dtype=torch.float64, device=self.device)])
+        self._epoch += 1                       # epoch of step n_from
+        self._acc = torch.empty(Ml, dtype=torch.int32, device=self.device)
+        rng = make_rng(self._seed, n_from, self._lo, None, None, 1)
+        kn = self.kernel.desc()
+        src = None if self._pending else self._src_local.data_ptr()
+        thr = float(self.ess_threshold) * self.M if self.ess_threshold is not None else 0.0
+        with torch.cuda.device(self.device):
+            L.check(lib.bk_smc_shard_run(self._model.handle, C.byref(self._sh()), src, n_from, n_to, self.N, C.byref(kn),
+                                         C.byref(rng), self._mode, thr, self._stats[k0].data_ptr(), self._acc.data_ptr(),
+                                         self._ws.data_ptr(), self._ws.numel(), stream_ptr(self.device)))
+        self._epoch += n_to - n_from           # epoch of step n_to
+        self._steps_taken.extend(range(n_from, n_to + 1))
+        self._pending = True
+        self.last_accept = self._acc
 
     def time(self, n: int) -> float:
         return n / self.N

@@ -325,6 +325,16 @@ BK_API int bk_smc_shard_move(uint64_t handle, const bk_smc_shard* sh, const void
 BK_API int bk_smc_shard_resample(const bk_smc_shard* sh, int32_t dtype, int32_t mode, const void* uniforms,
                           const bk_rng* rng, double ess_threshold, int32_t phase, double* stats_out,
                           void* ws, size_t ws_bytes, void* stream);
+/* run() (smc.py:39-41) for temperatures n_from..n_to in ONE call: move + resample of every step enqueued
+ * back to back from C (3 launches per temperature, no per-step host work -- at 8 GPUs a temperature of c4 is
+ * ~60 us of device time, less than two Python-level calls cost).  sh->epoch is the epoch of step n_from and
+ * advances by one per step (the caller continues with epoch + n_to - n_from + 1); Philox only (rng->mode),
+ * rng->draw_offset is ignored: step n draws with draw_offset = n, like the step-wise calls.
+ * stats_out: [n_to - n_from + 1, 4] doubles or NULL; accept_out: flags of the LAST step or NULL. */
+BK_API int bk_smc_shard_run(uint64_t handle, const bk_smc_shard* sh, const void* src_local, int32_t n_from,
+                     int32_t n_to, int32_t T, const bk_smc_kernel* kernel, const bk_rng* rng, int32_t mode,
+                     double ess_threshold, double* stats_out, int32_t* accept_out, void* ws, size_t ws_bytes,
+                     void* stream);
 /* thetas[idxs] (smc.py:75) materialised: out [n(rank), D] = rows idx[m] of the step-`epoch` arrays. */
 BK_API int bk_smc_shard_gather(const bk_smc_shard* sh, int64_t D, int32_t dtype, void* out, void* stream);
 

@@ -17,7 +17,7 @@ for mode in ("systematic", "multinomial"):
         smc.transition(1); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
         e0.record()
-        for n in range(2, T + 1): smc.transition(n)
+        smc.run_steps(2, T)
         e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     print(json.dumps({"M": M, "D": D, "T": T, "mode": mode, "layout": os.environ.get("BK_SMC_LAYOUT", "default"),
