@@ -41,7 +41,7 @@ class SmcKernel(C.Structure):
 
 class SmcShard(C.Structure):
     _fields_ = [("rank", i32), ("world", i32), ("M", i64), ("epoch", u64),
-                ("particles", (vp * SMC_MAX_WORLD) * 2), ("logw", vp * SMC_MAX_WORLD),
+                ("particles", (vp * SMC_MAX_WORLD) * 2), ("llpr", (vp * SMC_MAX_WORLD) * 2), ("logw", vp * SMC_MAX_WORLD),
                 ("idx", vp * SMC_MAX_WORLD), ("mailbox", vp * SMC_MAX_WORLD)]
 
 

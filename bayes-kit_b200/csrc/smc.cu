@@ -41,6 +41,11 @@ struct SmcArgs {
     uint64_t wait_done;        // > 0: wait until every rank's "indices of step wait_done are final" arrived
     double* maxpart;           // [gridDim.x] per-CTA maxima of the log-weights (NULL: no statistics epilogue)
     unsigned* ticket;
+    // (log_likelihood, log_prior) carried with the particle: written for every moved particle (llpr_out [M, 2]);
+    // read from the parent's pair (llpr_tab[owner][row]) instead of re-evaluating the model when carry != 0
+    T* llpr_out;
+    const T* llpr_tab[BK_SMC_MAX_WORLD];
+    int carry;
 };
 
 // ---- per-lane views of the LogPriorLikelihoodModel plugins (typing.py:37-42) ------------------
@@ -144,6 +149,13 @@ __global__ void __launch_bounds__(128, OCC ? OCC : (J >= 4 && sizeof(T) == 4) ? 
         shard_locate(a.sh, gid, r, loc);
         return a.src_tab[r] + loc * (int64_t)a.D;
     };
+    auto llpr_ptr = [&](int64_t gid) -> const T* {
+        if (!sharded) return a.llpr_tab[a.sh.world > 0 ? a.sh.rank : 0] + 2 * gid;
+        int r; int64_t loc;
+        shard_locate(a.sh, gid, r, loc);
+        return a.llpr_tab[r] + 2 * loc;
+    };
+    const bool carry = a.carry != 0;
     if (a.wait_done) {   // the indices (and the rows they point at) of the previous step are final on every rank
         if ((int)threadIdx.x < a.sh.world)
             mail_wait(a.mail_tab[a.sh.rank] + MB_DONE + (a.wait_done & 1) * BK_SMC_MAX_WORLD + threadIdx.x, a.wait_done,
@@ -153,7 +165,12 @@ __global__ void __launch_bounds__(128, OCC ? OCC : (J >= 4 && sizeof(T) == 4) ? 
     T nx[NE];                                  // particle of the next visit
     int64_t row_nn = 0;                        // resample index of the visit after that
     double lw_max = -INFINITY;
-    if (n_it > 0) ln.load(row_ptr(row_of(particle(0))), nx, T(0));
+    T nll = T(0), npr = T(0);                  // parent's (ll, prior) of the next visit
+    if (n_it > 0) {
+        const int64_t r0 = row_of(particle(0));
+        ln.load(row_ptr(r0), nx, T(0));
+        if (carry) { const T* lp2 = llpr_ptr(r0); nll = lp2[0]; npr = lp2[1]; }
+    }
     if (n_it > 1) row_nn = row_of(particle(1));
     const T t0 = a.t0;
     auto tgrad = [&](const T (&x)[NE], int k) { return A::add(A::mul(md.gll(x, k), t0), md.gpr(x, k)); };
@@ -164,8 +181,12 @@ __global__ void __launch_bounds__(128, OCC ? OCC : (J >= 4 && sizeof(T) == 4) ? 
         T th[NE], z[NE], st[NE];
 #pragma unroll
         for (int k = 0; k < NE; ++k) th[k] = nx[k];
+        T ll_c = nll, pr_c = npr;
         // thetas[idxs] of the previous importance_resample (smc.py:75) is folded into this read
-        if (it + 1 < n_it) ln.load(row_ptr(row_nn), nx, T(0));
+        if (it + 1 < n_it) {
+            ln.load(row_ptr(row_nn), nx, T(0));
+            if (carry) { const T* lp2 = llpr_ptr(row_nn); nll = lp2[0]; npr = lp2[1]; }
+        }
         if (it + 2 < n_it) row_nn = row_of(particle(it + 2));
         uint32_t raw2[2] = {0u, 0u};
         ln.normals(a.rng, a.M, m, 0, z, raw2);
@@ -183,8 +204,8 @@ __global__ void __launch_bounds__(128, OCC ? OCC : (J >= 4 && sizeof(T) == 4) ? 
             if (ln.lane == 0) lu = log_u(ln.uniform(a.rng, a.M, m, 0, 0));
             lu = __shfl_sync(0xffffffffu, lu, 0, G);
         }
-        T ll_c, pr_c, ll_s, pr_s;
-        md.terms(th, ll_c, pr_c);
+        T ll_s, pr_s;
+        if (!carry) md.terms(th, ll_c, pr_c);       // first step / replaced particles: nothing carried yet
         const T lp_c = A::add(A::mul(ll_c, t0), pr_c);
         bool acc;
         if constexpr (MOVE == BK_SMC_KERNEL_RW) {
@@ -255,6 +276,7 @@ __global__ void __launch_bounds__(128, OCC ? OCC : (J >= 4 && sizeof(T) == 4) ? 
         if (active) {
             ln.store(a.thetas + m * (int64_t)a.D, th);
             if (ln.lane == 0) {
+                if (a.llpr_out) { a.llpr_out[2 * m] = ll_c; a.llpr_out[2 * m + 1] = pr_c; }
                 const T lw_tot = a.logw_prev ? A::add(a.logw_prev[m], lw) : lw;
                 a.logw[m] = lw_tot;
                 lw_max = fmax(lw_max, (double)lw_tot);
@@ -1021,7 +1043,8 @@ static int make_geom(const bk_smc_shard* sh, ShardGeom* g) {
     g->extra = (int32_t)(sh->M % sh->world);
     g->small = sh->M < (1ll << 32) ? 1 : 0;
     for (int r = 0; r < sh->world; ++r)
-        BK_CHECK_ARG(sh->mailbox[r] && sh->logw[r] && sh->idx[r] && sh->particles[0][r] && sh->particles[1][r],
+        BK_CHECK_ARG(sh->mailbox[r] && sh->logw[r] && sh->idx[r] && sh->particles[0][r] && sh->particles[1][r] &&
+                         sh->llpr[0][r] && sh->llpr[1][r],
                      "bk_smc_shard: rank %d has a null buffer", r);
     return BK_OK;
 }
@@ -1219,8 +1242,11 @@ static int shard_move_t(const Model& m, const bk_smc_shard* sh, const ShardGeom&
     a.sh = g;
     for (int r = 0; r < g.world; ++r) {
         a.src_tab[r] = (const T*)sh->particles[prev][r];
+        a.llpr_tab[r] = (const T*)sh->llpr[prev][r];
         a.mail_tab[r] = (uint64_t*)sh->mailbox[r];
     }
+    a.llpr_out = (T*)sh->llpr[cur][g.rank];
+    a.carry = src_local ? 0 : 1;
     if (src_local) {
         a.src = (const T*)src_local;
         a.src_idx = nullptr;

@@ -150,7 +150,8 @@ class TemperedLikelihoodSMC:
         es = 4 if self.dtype == torch.float32 else 8
         n_max = -(-self.M // self._world)
         key = f"smc{id(self) if not isinstance(group, P_.FakeRank) else ''}:{self.M}:{self.D}:{es}"
-        self._mem = P_.PeerRegion(key, {"p0": n_max * self.D * es, "p1": n_max * self.D * es, "logw": n_max * es,
+        self._mem = P_.PeerRegion(key, {"p0": n_max * self.D * es, "p1": n_max * self.D * es, "l0": n_max * 2 * es,
+                                        "l1": n_max * 2 * es, "logw": n_max * es,
                                         "idx": n_max * 8, "mail": L.SMC_MAILBOX_BYTES}, self.device, group)
         nl = self._hi - self._lo
         self._parts = [self._mem.tensor("p0", self.dtype, (nl, self.D)), self._mem.tensor("p1", self.dtype, (nl, self.D))]
@@ -170,7 +171,8 @@ class TemperedLikelihoodSMC:
         if self._shard is None:
             s = L.SmcShard()
             s.rank, s.world, s.M = self._rank, self._world, self.M
-            for name, field in (("p0", s.particles[0]), ("p1", s.particles[1]), ("logw", s.logw), ("idx", s.idx),
+            for name, field in (("p0", s.particles[0]), ("p1", s.particles[1]), ("l0", s.llpr[0]), ("l1", s.llpr[1]),
+                                ("logw", s.logw), ("idx", s.idx),
                                 ("mail", s.mailbox)):
                 for r, p in enumerate(self._mem.ptrs(name)):
                     field[r] = p

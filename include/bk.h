@@ -301,6 +301,10 @@ typedef struct bk_smc_shard {
                                                      same on every rank)                             */
     void*    particles[2][BK_SMC_MAX_WORLD];      /* every rank's two particle arrays [n(r), D]:
                                                      step e writes [e & 1], reads [(e - 1) & 1]      */
+    void*    llpr[2][BK_SMC_MAX_WORLD];           /* every rank's (log_likelihood, log_prior) pairs
+                                                     [n(r), 2] of the particles in the same-numbered
+                                                     particle array: a move starts from its parent's
+                                                     pair instead of re-evaluating the model         */
     void*    logw[BK_SMC_MAX_WORLD];              /* every rank's log-weights [n(r)]                 */
     int64_t* idx[BK_SMC_MAX_WORLD];               /* every rank's resample indices [n(r)], global ids */
     void*    mailbox[BK_SMC_MAX_WORLD];           /* every rank's mailbox (BK_SMC_MAILBOX_BYTES)      */

@@ -51,9 +51,12 @@ def leg_c2_mala(hbm, tf):
     s = bk.MALA(bk.DensePrecGauss(c2_precision()), 2e-3, chains=C, seed=0)
     ms = _timed(lambda: s.sample_n(1), reps=10, warm=3)
     v = C / (ms * 1e-3)
+    # a MALA draw = begin (18 B per element) + one 3-pass tcgen05 gradient (10 B) + end (24 B): the row kernels'
+    # HBM streams bound it, the GEMM is 0.3 of the 1.07 ms
     return {"workload": f"c2: MALA eps=2e-3, {C} chains x {D}-dim dense-precision Gaussian, fp32 Philox", "value": v,
             "unit": "chain-steps/s", "ms": ms, "accept_rate": float(s.last_accept.float().mean()),
-            "roofline": _roof("tensor", 2.0 * C * D * D / (ms * 1e-3) / 1e12, tf, "TFLOP/s")}
+            "roofline": _roof("hbm", 52.0 * C * D / (ms * 1e-3) / 1e9, hbm, "GB/s"),
+            "tensor_side": _roof("tensor", 3 * 2.0 * C * D * D / (ms * 1e-3) / 1e12, tf, "TFLOP/s")}
 
 
 def leg_c3(rank, world, tf):
