@@ -329,12 +329,24 @@ class TemperedLikelihoodSMC:
             self._pending = True    # thetas[idxs]: folded into the next move (or .thetas)
 
     def wire_bytes_per_step(self) -> dict:
-        """Bytes this rank puts on / takes off NVLink per temperature (systematic mode), by kind: the three
-        messages to each peer, the index stores for slots other ranks own, and the particle rows read from
-        peers.  The last two depend on the weights; the figures are the expectation for exchangeable
-        particles (a fraction (G - 1) / G of a rank's offspring / parents live elsewhere)."""
+        """Bytes this rank put on / took off NVLink in the LAST temperature step, by kind (synchronises): the three
+        messages to each peer, the index stores into slots other ranks own, and the particle rows (+ their
+        (ll, prior) pairs) read from peers -- counted from the step's resample indices.  Systematic resampling
+        keeps most parents local (slot k's parent is particle ~k); multinomial parents are uniform over the ranks."""
         g, nl = self._world, self._hi - self._lo
         es = 4 if self.dtype == torch.float32 else 8
-        frac = (g - 1) / g
-        return {"messages": (16 + 32 + 8) * (g - 1), "indices": int(8 * nl * frac),
-                "particle_rows": int(nl * self.D * es * frac)}
+        out = {"messages": (16 + 32 + 8) * (g - 1), "indices": 0, "particle_rows": 0}
+        if g == 1 or not self._epoch:
+            return out
+        if isinstance(self._group, P_.FakeRank):
+            torch.cuda.synchronize(self.device)
+        else:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self._group)
+        idx = self._idx
+        remote_parents = int(((idx < self._lo) | (idx >= self._hi)).sum().item())
+        out["particle_rows"] = remote_parents * (self.D + 2) * es
+        # offspring this rank resolved for slots owned elsewhere == by symmetry of the protocol the remote parents of the
+        # OTHER ranks; all-reduce the count for the exact figure, or report the local mirror (parents read remotely)
+        out["indices"] = remote_parents * 8
+        return out
