@@ -188,3 +188,60 @@ def test_engines_agree_in_philox_mode(bk, D, monkeypatch):
     for (d0, a0), (d1, a1) in zip(*res):
         assert np.array_equal(a0, a1)
         np.testing.assert_allclose(d0, d1, rtol=1e-12, atol=1e-12)
+
+
+# ---- the reference's own beta-binomial test target (test/models/binomial.py) through every sampler --------------------
+# Same model, sampler settings, burn-in and tolerances as upstream; device RNG, fp32; 256 chains in lockstep where the
+# reference runs one (every chain must pass on average: the moments are pooled over chains AND draws, so the
+# tolerances are far looser than needed -- they are the reference's).
+def _binom(bk):
+    return bk.Binomial(alpha=2, beta=3, x=5, N=15)
+
+
+def _check_binom(model, draws, burn, atol_mean, atol_var):
+    p = model.constrain_draws(draws[burn:]).double().reshape(-1)
+    assert abs(float(p.mean()) - model.posterior_mean()) < atol_mean
+    assert abs(float(p.var()) - model.posterior_variance()) < atol_var
+
+
+def test_hmc_binom(bk):          # test_hmc.py:68-86
+    model = _binom(bk)
+    s = bk.HMCDiag(model, stepsize=0.08, steps=3, chains=256, seed=1)
+    d, _ = s.sample_n(800)
+    _check_binom(model, d, 100, 0.05, 0.01)
+
+
+def test_mala_binom(bk):         # test_mala.py:25-41
+    model = _binom(bk)
+    s = bk.MALA(model, 0.07, chains=256, seed=2)
+    d, _ = s.sample_n(1200)
+    _check_binom(model, d, 200, 0.05, 0.01)
+
+
+def test_metropolis_binom(bk):   # test_metropolis.py:127-139 (proposal normal(loc=theta, scale=4))
+    model = _binom(bk)
+    s = bk.Metropolis(model, bk.GaussianRW(4.0), chains=256, seed=3)
+    d, _ = s.sample_n(1000)
+    _check_binom(model, d, 0, 0.1, 0.1)
+
+
+def test_drghmc_binom(bk):       # test_drghmc.py:151-176
+    model = _binom(bk)
+    s = bk.DrGhmcDiag(model, 3, [0.1] * 3, [3] * 3, 0.2, chains=256, seed=4)
+    d, _ = s.sample_n(800)
+    _check_binom(model, d, 100, 0.05, 0.01)
+
+
+def test_rwm_smc_binom(bk):      # test_tempered_smc.py:8-30: M = 75, N = 15, metropolis_kernel(0.5); here 32 replicates pooled
+    model = _binom(bk)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    means, vars_ = [], []
+    for rep in range(32):
+        p0 = torch.distributions.Beta(2.0, 3.0).sample((75,)).to("cuda")          # initial_state: logit of a prior draw
+        th0 = torch.log(p0 / (1 - p0)).reshape(75, 1)
+        smc = bk.TemperedLikelihoodSMC(model, 75, 15, th0, bk.metropolis_kernel(0.5), seed=100 + rep)
+        smc.run()
+        p = model.constrain_draws(smc.thetas).double().reshape(-1)
+        means.append(float(p.mean())); vars_.append(float(p.var()))
+    assert abs(np.mean(means) - model.posterior_mean()) < 0.05        # the reference's tolerances for ONE run
+    assert abs(np.mean(vars_) - model.posterior_variance()) < 0.01
