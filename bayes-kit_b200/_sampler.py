@@ -279,10 +279,10 @@ class ChainSampler:
         """``n`` draws of every chain with HOST buffers -- what a caller of the reference ends up with after
         ``[sampler.sample() for _ in range(n)]`` (host arrays, hmc.py:63): the chain state goes in ONCE
         (``theta_host`` [C, D], optional), all n draws and log densities come back
-        (``out = (draws_host [n, C, D], logp_host [n, C])``, pinned; allocated when None).  Chains are cut into
-        chunks; chunk k's device->host copies, chunk k+1's kernels (n draws) and chunk k+2's host->device copy
-        run concurrently on three streams, with a ring of three device staging buffers.  Chunking cannot change
-        the result (Philox is keyed by the global chain id).  Returns (draws_host, logp_host), complete on
+        (``out = (draws_host [n, C, D], logp_host [n, C])``, pinned; allocated when None).  The pipeline runs over
+        DRAWS: draw t's device->host copy overlaps draw t+1's kernels (all chains at once, a ring of three device
+        staging buffers); only the first draw is cut into chain chunks so that the host->device copy of the state
+        overlaps its kernels.  Neither can change the result (Philox is keyed by global chain id and draw index).  Returns (draws_host, logp_host), complete on
         return; ``last_accept`` [n, C] stays on the device."""
         if self._single:
             raise ValueError("sample_host_n is the batched surface: construct with init [C, D] or chains=C")
@@ -305,12 +305,14 @@ class ChainSampler:
                 chunk_chains = max(256, int(round(9472 * 1000 / max(D, 1) / 256)) * 256)
             chunk_chains = max(1, min(int(chunk_chains), C_))
             sizes = [min(chunk_chains, C_ - c) for c in range(0, C_, chunk_chains)]
-        cmax = max(sizes)
+        # Pipeline over DRAWS: the device -> host copy of draw t (C * D * 4 bytes) runs while draw t + 1 is computed for
+        # ALL chains at full kernel efficiency; only the first draw is chunked over chains, so that the host -> device
+        # copy of the state overlaps its kernels.  The D2H stream is the critical path (a draw leaves in ~4.8 ms over
+        # PCIe 5 x16, its kernels take ~3 ms at c2) and it starts after ~one chunk of the first draw.
         ring = getattr(self, "_hn_ring", None)
-        if ring is None or ring[0][0].shape[0] < n or ring[0][0].shape[1] < cmax:
-            ring = [(torch.empty(n, cmax, D, dtype=self.dtype, device=self.device),
-                     torch.empty(n, cmax, dtype=self.dtype, device=self.device),
-                     torch.empty(n, cmax, dtype=torch.int32, device=self.device)) for _ in range(3)]
+        if ring is None:
+            ring = [(torch.empty(C_, D, dtype=self.dtype, device=self.device),
+                     torch.empty(C_, dtype=self.dtype, device=self.device)) for _ in range(3)]
             self._hn_ring = ring
         if getattr(self, "_hs", None) is None:
             self._hs = tuple(torch.cuda.Stream(self.device) for _ in range(3))
@@ -321,36 +323,46 @@ class ChainSampler:
         stale = theta_host is not None or not self._cache_valid.value
         acc_all = torch.empty(n, C_, dtype=torch.int32, device=self.device)
         freed = [None, None, None]      # event: the ring slot's previous contents have left for the host
-        c0 = 0
-        for k, cn in enumerate(sizes):
-            slot = k % 3
-            valid = L.i32(0 if stale else 1)
-            if theta_host is not None:
-                with torch.cuda.stream(s_in):
-                    self._theta[c0:c0 + cn].copy_(theta_host[c0:c0 + cn], non_blocking=True)
-                s_run.wait_stream(s_in)
+        for t in range(n):
+            slot = t % 3
+            sd, sl = ring[slot]
             if freed[slot] is not None:
                 s_run.wait_event(freed[slot])
-            # staging laid out [n, cn, D] for THIS chunk (the kernels see cn chains)
-            sd = ring[slot][0].view(-1)[: n * cn * D].view(n, cn, D)
-            sl = ring[slot][1].view(-1)[: n * cn].view(n, cn)
-            sa = ring[slot][2].view(-1)[: n * cn].view(n, cn)
-            with torch.cuda.stream(s_run):
-                rng = make_rng(self._seed, self._t, self._chain_offset + c0, None, None, self._n_uniform)
-                o = L.DrawOut(sd.data_ptr(), sl.data_ptr(), sa.data_ptr())
-                self._launch(n, rng, o, c0, cn, valid)
-                acc_all[:, c0:c0 + cn].copy_(sa, non_blocking=True)
-                done = torch.cuda.Event()
-                done.record(s_run)
-            s_out.wait_event(done)
+            if t == 0:
+                c0 = 0
+                for k, cn in enumerate(sizes):
+                    valid = L.i32(0 if stale else 1)
+                    if theta_host is not None:
+                        with torch.cuda.stream(s_in):
+                            self._theta[c0:c0 + cn].copy_(theta_host[c0:c0 + cn], non_blocking=True)
+                        s_run.wait_stream(s_in)
+                    with torch.cuda.stream(s_run):
+                        rng = make_rng(self._seed, self._t, self._chain_offset + c0, None, None, self._n_uniform)
+                        o = L.DrawOut(sd[c0:].data_ptr(), sl[c0:].data_ptr(), acc_all[0, c0:].data_ptr())
+                        self._launch(1, rng, o, c0, cn, valid)
+                        done = torch.cuda.Event()
+                        done.record(s_run)
+                    s_out.wait_event(done)
+                    with torch.cuda.stream(s_out):
+                        draws_h[0, c0:c0 + cn].copy_(sd[c0:c0 + cn], non_blocking=True)
+                        logp_h[0, c0:c0 + cn].copy_(sl[c0:c0 + cn], non_blocking=True)
+                    c0 += cn
+                self._cache_valid.value = 1
+            else:
+                with torch.cuda.stream(s_run):
+                    rng = make_rng(self._seed, self._t + t, self._chain_offset, None, None, self._n_uniform)
+                    o = L.DrawOut(sd.data_ptr(), sl.data_ptr(), acc_all[t].data_ptr())
+                    self._launch(1, rng, o, 0, C_, L.i32(1))
+                    done = torch.cuda.Event()
+                    done.record(s_run)
+                s_out.wait_event(done)
+                with torch.cuda.stream(s_out):
+                    draws_h[t].copy_(sd, non_blocking=True)
+                    logp_h[t].copy_(sl, non_blocking=True)
             with torch.cuda.stream(s_out):
-                for t in range(n):
-                    draws_h[t, c0:c0 + cn].copy_(sd[t], non_blocking=True)
-                    logp_h[t, c0:c0 + cn].copy_(sl[t], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(s_out)
                 freed[slot] = ev
-            c0 += cn
         self._t += n
         self.last_accept = acc_all
         self._cache_valid.value = 1
