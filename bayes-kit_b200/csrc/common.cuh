@@ -139,6 +139,31 @@ __host__ __device__ __forceinline__ double u01d(uint32_t hi, uint32_t lo) {
     return (((double)(hi >> 6)) * 67108864.0 + (double)(lo >> 6) + 0.5) * 2.220446049250313e-16;
 }
 
+// Box-Muller on the SFU, fp32, straight from the counter-mode words (no intermediate u01 grid): ~6 instructions per
+// normal.  Radius: u = (w + 0.5) 2^-32 rounded to fp32, in (0, 1] (2^-33 at w = 0: |z| <= 6.8; exactly 1 with
+// probability 2^-25: radius 0), r = sqrt(-2 ln u) by lg2.approx / sqrt.approx (u is never denormal, so none of the
+// range fix-ups of logf / sqrtf are needed).  Angle: the word read as a SIGNED integer times 2 pi / 2^32, i.e. already
+// folded into [-pi, pi], where sin.approx / cos.approx have ~2^-21 absolute error -- far below fp32 sampling noise.
+__device__ __forceinline__ float bm_radius(uint32_t w) {
+    const float u = fmaf(__uint2float_rn(w), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    float l, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * -1.3862943611198906f));
+    return r;
+}
+__device__ __forceinline__ void bm_sincos(uint32_t w, float& s, float& c) {
+    const float a = __int2float_rn((int32_t)w) * 1.4629180792671596e-9f;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(a));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(a));
+}
+__device__ __forceinline__ void box_muller4(const uint32_t (&r)[4], float (&z)[4]) {
+    const float r0 = bm_radius(r[0]), r1 = bm_radius(r[2]);
+    float s0, c0, s1, c1;
+    bm_sincos(r[1], s0, c0);
+    bm_sincos(r[3], s1, c1);
+    z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+}
+
 // 4 standard normals for element block `block` of (chain, draw)
 // (raw2, when given, receives the first two counter-mode words of the block: a caller whose block
 // holds no valid element may spend them on something else, e.g. an accept uniform)
@@ -151,13 +176,7 @@ __device__ __forceinline__ void philox_normal4<float>(uint64_t seed, uint32_t bl
     uint32_t r[4];
     Philox::gen(seed, block, TAG_NORMAL, chain, draw, r);
     if (raw2) { raw2[0] = r[0]; raw2[1] = r[1]; }
-    // Box-Muller on the SFU: __logf / __sincosf have ~2^-21 absolute error on these
-    // ranges (angle folded into [-pi, pi)) -- far below the fp32 sampling noise.
-    float r0 = sqrtf(-2.0f * __logf(u01(r[0]))), r1 = sqrtf(-2.0f * __logf(u01(r[2])));
-    float s0, c0, s1, c1;
-    __sincosf(6.2831853071795865f * (u01(r[1]) - 0.5f), &s0, &c0);
-    __sincosf(6.2831853071795865f * (u01(r[3]) - 0.5f), &s1, &c1);
-    z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+    box_muller4(r, z);
 }
 template <>
 __device__ __forceinline__ void philox_normal4<double>(uint64_t seed, uint32_t block, uint32_t chain,
@@ -192,18 +211,12 @@ __device__ __forceinline__ double philox_uniform<double>(uint64_t seed, uint32_t
     return (k & 1) ? u01d(r[2], r[3]) : u01d(r[0], r[1]);
 }
 
-// Accept uniform of the single-uniform samplers (HMC / MALA / RW-Metropolis) in Philox mode.
-// The fused register-resident kernels lay a chain out over sep_slots(D) blocks of 4 elements; when the
-// LAST block is pure padding (4 (slots - 1) >= D) its normal-stream Philox words are unused by the
-// proposal and serve as the accept uniform -- one counter-mode call per lane and draw instead of two.
-// Every engine follows the same rule (this function), so chains do not depend on which engine ran.
-__host__ __device__ __forceinline__ int sep_slots(int D) {
-    return D <= 4 ? 1 : D <= 16 ? 4 : D <= 32 ? 8 : D <= 64 ? 16 : D <= 128 ? 32 : D <= 256 ? 64 : D <= 512 ? 128 : 0;
-}
-__host__ __device__ __forceinline__ bool accept_uniform_from_spare_block(int D) {
-    const int s = sep_slots(D);
-    return s > 0 && 4 * (s - 1) >= D;
-}
+// Accept uniform of the single-uniform samplers (HMC / MALA / RW-Metropolis) in Philox mode: the first words of
+// element block B = ceil(D / 4) of the NORMAL stream -- the first block no element of the proposal uses.  A fused
+// register-resident kernel whose lane layout has a slot for block B gets it from the pass that makes the normals
+// (one counter-mode call per lane and draw instead of two); every other engine makes one extra call.  The rule
+// does not depend on the layout, so chains do not depend on which engine (or lane layout) ran.
+__host__ __device__ __forceinline__ int accept_block(int D) { return (D + 3) >> 2; }
 template <typename T>
 __device__ __forceinline__ T uniform_of_words(uint32_t w0, uint32_t w1) {
     if constexpr (sizeof(T) == 4) return u01(w0);
@@ -211,12 +224,9 @@ __device__ __forceinline__ T uniform_of_words(uint32_t w0, uint32_t w1) {
 }
 template <typename T>
 __device__ __forceinline__ T philox_accept_uniform(uint64_t seed, uint32_t chain, uint32_t draw, int D) {
-    if (accept_uniform_from_spare_block(D)) {
-        uint32_t r[4];
-        Philox::gen(seed, (uint32_t)(sep_slots(D) - 1), TAG_NORMAL, chain, draw, r);
-        return uniform_of_words<T>(r[0], r[1]);
-    }
-    return philox_uniform<T>(seed, 0u, chain, draw);
+    uint32_t r[4];
+    Philox::gen(seed, (uint32_t)accept_block(D), TAG_NORMAL, chain, draw, r);
+    return uniform_of_words<T>(r[0], r[1]);
 }
 
 // ---- reductions over a group of G consecutive lanes (G power of two <= 32) ---

@@ -84,9 +84,10 @@ struct Lanes {
         }
     }
     // standard normals for (chain, draw); invalid slots are 0
-    // raw2 (optional): the first two Philox words of this lane's LAST block (j = J - 1)
+    // raw2 (optional): the first two Philox words of element block `ub`, left in the lane that owns that block
+    // (lane ub % G) -- the accept uniform of common.cuh's rule when the layout has a slot for it (ub < G * J)
     __device__ __forceinline__ void normals(const bk_rng& rng, int64_t C, int64_t chain, int64_t t,
-                                            T (&z)[NE], uint32_t* raw2 = nullptr) const {
+                                            T (&z)[NE], uint32_t* raw2 = nullptr, int ub = -1) const {
         if (rng.mode == BK_RNG_INJECTED) {
             load(reinterpret_cast<const T*>(rng.normals) + (t * C + chain) * (int64_t)D, z, T(0));
         } else {
@@ -96,7 +97,9 @@ struct Lanes {
             for (int j = 0; j < J; ++j) {
                 int blk = lane + G * j;
                 T q[4];
-                philox_normal4<T>(rng.seed, (uint32_t)blk, gc, gd, q, j == J - 1 ? raw2 : nullptr);
+                uint32_t w[2];
+                philox_normal4<T>(rng.seed, (uint32_t)blk, gc, gd, q, w);
+                if (raw2 && blk == ub) { raw2[0] = w[0]; raw2[1] = w[1]; }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) z[4 * j + i] = (4 * blk + i < D) ? q[i] : T(0);
             }

@@ -137,7 +137,8 @@ __global__ void __launch_bounds__(128, OCC ? OCC : (J >= 4 && sizeof(T) == 4) ? 
     ln.vec2 = a.vec2 != 0;
     View<T, G, J> md;
     md.init(a, ln);
-    const bool spare_block = a.rng.mode == BK_RNG_PHILOX && 4 * (G * J - 1) >= a.D;
+    const int ub = accept_block(a.D);   // common.cuh: the accept uniform = words of element block ceil(D / 4) of the normal stream
+    const bool spare_block = a.rng.mode == BK_RNG_PHILOX && ub < G * J;
     auto particle = [&](int64_t it) { const int64_t r = g0 + it * n_groups; return r < a.M ? r : a.M - 1; };
     auto row_of = [&](int64_t m) { return a.src_idx ? a.src_idx[m] : m; };
     // sharded source: the resample indices are global particle ids; the row is read from its owner's
@@ -189,19 +190,23 @@ __global__ void __launch_bounds__(128, OCC ? OCC : (J >= 4 && sizeof(T) == 4) ? 
         }
         if (it + 2 < n_it) row_nn = row_of(particle(it + 2));
         uint32_t raw2[2] = {0u, 0u};
-        ln.normals(a.rng, a.M, m, 0, z, raw2);
-        // accept uniform: when the group's last element block is pure padding (4 (G J - 1) >= D), its
-        // Philox words are unused by the proposal and serve as the uniform -- one counter-mode call per
-        // lane and particle instead of two.  Otherwise (and for injected streams) the dedicated stream.
+        ln.normals(a.rng, a.M, m, 0, z, raw2, ub);
+        // accept uniform: when the lane layout has a slot for block ub, the pass above made its Philox words --
+        // one counter-mode call per lane and particle instead of two.  Otherwise one extra call (same block);
+        // injected streams: the recorded uniform.
         T lu = T(0);
         if (spare_block) {
-            if (ln.lane == G - 1) {
+            if (ln.lane == ub % G) {
                 if constexpr (sizeof(T) == 4) lu = log_u(u01(raw2[0]));
                 else lu = log_u(u01d(raw2[0], raw2[1]));
             }
-            lu = __shfl_sync(0xffffffffu, lu, G - 1, G);
+            lu = __shfl_sync(0xffffffffu, lu, ub % G, G);
         } else {
-            if (ln.lane == 0) lu = log_u(ln.uniform(a.rng, a.M, m, 0, 0));
+            if (ln.lane == 0)
+                lu = log_u(a.rng.mode == BK_RNG_PHILOX
+                               ? philox_accept_uniform<T>(a.rng.seed, (uint32_t)(a.rng.chain_offset + (uint64_t)m),
+                                                          (uint32_t)a.rng.draw_offset, a.D)
+                               : ln.uniform(a.rng, a.M, m, 0, 0));
             lu = __shfl_sync(0xffffffffu, lu, 0, G);
         }
         T ll_s, pr_s;
