@@ -475,11 +475,42 @@ int hlr_tc_splits(int64_t C, int64_t N) {
     return (int)(want < 1 ? 1 : want);
 }
 
+constexpr int HLR_MAX_FUSED_STEPS = 32;    // leapfrog steps per persistent launch (counters reserved in the workspace)
+static size_t hlr_steps_cnt_words(int64_t C) {
+    const int64_t ctiles = (C + CT - 1) / CT;
+    return ctiles <= 148 ? (size_t)HLR_MAX_FUSED_STEPS * ctiles * 2 + 64 : 0;
+}
+
 size_t hlr_tc_eval_ws_bytes(const Model& m, int64_t C) {
     const int Dx = (int)m.d.dims - 2;
     const int ns = hlr_tc_splits(C, m.d.n_obs);
     return 2 * align_up((size_t)pad128(C) * KJ * 2, 256) + align_up((size_t)ns * C * Dx * 4, 256) +
-           align_up((size_t)ns * C * 4, 256) + 1024;
+           align_up((size_t)ns * C * 4, 256) + align_up(hlr_steps_cnt_words(C) * 4, 256) + 1024;
+}
+
+// one layout of the evaluation workspace for every entry point (the bf16 operand written by one call is read by the next)
+struct HlrWs {
+    __nv_bfloat16 *bb, *bl;   // operand beta (hi, lo) [Cp, 128]
+    float *pg, *pl;           // per-slice partial gradients [ns, C, Dx] / log-likelihoods [ns, C]
+    uint32_t* cnt;            // counters of the multi-step launch + error word
+    int ns;
+    bool ok;
+    size_t need;
+};
+static HlrWs hlr_carve(const Model& m, int64_t C, void* ws, size_t ws_bytes) {
+    const int Dx = (int)m.d.dims - 2;
+    const int64_t Cp = pad128(C);
+    HlrWs w;
+    w.ns = hlr_tc_splits(C, m.d.n_obs);
+    Arena ar(ws, ws_bytes);
+    w.bb = ar.take<__nv_bfloat16>((size_t)Cp * KJ);
+    w.bl = ar.take<__nv_bfloat16>((size_t)Cp * KJ);
+    w.pg = ar.take<float>((size_t)w.ns * C * Dx);
+    w.pl = ar.take<float>((size_t)w.ns * C);
+    w.cnt = ar.take<uint32_t>(hlr_steps_cnt_words(C));
+    w.ok = ar.ok();
+    w.need = ar.off;
+    return w;
 }
 
 // partial gradients / log-likelihoods of every observation slice -> part_g, part_ll
@@ -490,13 +521,11 @@ int hlr_tc_partial(const Model& m, const float* theta, int64_t C, void* ws, size
                    __nv_bfloat16** operand) {
     const int D = (int)m.d.dims, Dx = D - 2;
     const int64_t N = m.d.n_obs, Np = pad128(N), Cp = pad128(C);
-    const int ns = hlr_tc_splits(C, N);
-    Arena ar(ws, ws_bytes);
-    __nv_bfloat16* bb = ar.take<__nv_bfloat16>((size_t)Cp * KJ);
-    __nv_bfloat16* bl = ar.take<__nv_bfloat16>((size_t)Cp * KJ);
-    float* pg = ar.take<float>((size_t)ns * C * Dx);
-    float* pl = ar.take<float>((size_t)ns * C);
-    if (!ar.ok()) { set_error("model eval workspace too small (%zu < %zu)", ws_bytes, ar.off); return BK_E_WORKSPACE; }
+    const HlrWs w = hlr_carve(m, C, ws, ws_bytes);
+    if (!w.ok) { set_error("model eval workspace too small (%zu < %zu)", ws_bytes, w.need); return BK_E_WORKSPACE; }
+    const int ns = w.ns;
+    __nv_bfloat16 *bb = w.bb, *bl = w.bl;
+    float *pg = w.pg, *pl = w.pl;
     if (operand) *operand = bb;
     if (!operand_ready) {
         // gradient-only mode folds the 1/2 of sigmoid(z) = 1/2 + tanh(z/2)/2 into the operand (exact in bf16)
@@ -542,40 +571,57 @@ int hlr_tc_partial(const Model& m, const float* theta, int64_t C, void* ws, size
 // gradient), the leapfrog kick and drift  r += eps m g ; q += eps r  (hmc.py:48-49), and the bf16
 // operand (beta / 2, zero padded) of the NEXT gradient launch -- instead of three kernels
 // (finish, step, operand preparation) and two round trips of the gradient through HBM.
-__global__ void k_hlr_finish_step(float* __restrict__ q, float* __restrict__ r, const float* __restrict__ part_g,
-                                  int64_t C, int Dx, int D, int n_split, float eps, const float* __restrict__ metric,
-                                  __nv_bfloat16* __restrict__ operand) {
-    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (c >= C) return;
-    float* th = q + c * D;
-    float* rr = r + c * D;
+// The partial sums of two dimensions per lane (up to 32 loads) are requested before any is consumed: inside the
+// multi-step kernel below this runs on the critical path of every leapfrog step.  Slices are summed in a fixed
+// order (four interleaved accumulators over the full groups of 4, the remainder into the first), independent of
+// which kernel calls it.
+__device__ __forceinline__ void hlr_finish_chain(float* __restrict__ th, float* __restrict__ rr,
+                                                 const float* __restrict__ pg_chain, int64_t step, int Dx,
+                                                 int n_split, float eps, const float* __restrict__ metric,
+                                                 __nv_bfloat16* __restrict__ oprow, int lane, bool poison) {
     const float mu = th[Dx], lam = th[Dx + 1];
     const float e2 = expf(-2.f * lam), ep2 = expf(2.f * lam);
     float sr = 0.f, ss = 0.f;
-    const int64_t step = C * (int64_t)Dx;
-    for (int j = lane; j < KJ; j += 32) {
-        float bq = 0.f;
-        if (j < Dx) {
-            const float d = th[j] - mu;
-            sr += d;
-            ss = fmaf(d, d, ss);
-            float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
-            const float* pg = part_g + c * Dx + j;
-            int s = 0;
-            for (; s + 4 <= n_split; s += 4) {
-                const float a0 = pg[(s + 0) * step], a1 = pg[(s + 1) * step], a2 = pg[(s + 2) * step],
-                            a3 = pg[(s + 3) * step];
-                g0 += a0; g1 += a1; g2 += a2; g3 += a3;
+    const int ns4 = n_split & ~3;
+#pragma unroll 1
+    for (int jp = 0; jp < KJ / 64; ++jp) {
+        float g[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll 1
+        for (int s0 = 0; s0 < n_split; s0 += 16) {
+            float av[2][16];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = lane + 32 * (2 * jp + h);
+#pragma unroll
+                for (int u = 0; u < 16; ++u)
+                    av[h][u] = (j < Dx && s0 + u < n_split) ? __ldcg(pg_chain + j + (int64_t)(s0 + u) * step) : 0.f;
             }
-            for (; s < n_split; ++s) g0 += pg[s * step];
-            const float g = ((g0 + g1) + (g2 + g3)) - e2 * d;
-            const float rn = fmaf(eps * (metric ? metric[j] : 1.f), g, rr[j]);
-            rr[j] = rn;
-            bq = fmaf(eps, rn, th[j]);
-            th[j] = bq;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    if (s0 + u < ns4) g[h][u & 3] += av[h][u];
+                    else if (s0 + u < n_split) g[h][0] += av[h][u];
+                }
+            }
         }
-        operand[c * KJ + j] = __float2bfloat16_rn(0.5f * bq);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = lane + 32 * (2 * jp + h);
+            float bq = 0.f;
+            if (j < Dx) {
+                const float d = th[j] - mu;
+                sr += d;
+                ss = fmaf(d, d, ss);
+                const float gs = ((g[h][0] + g[h][1]) + (g[h][2] + g[h][3])) - e2 * d;
+                const float rn = fmaf(eps * (metric ? metric[j] : 1.f), gs, rr[j]);
+                rr[j] = rn;
+                bq = fmaf(eps, rn, th[j]);
+                if (poison) bq = __int_as_float(0x7fc00000);
+                th[j] = bq;
+            }
+            oprow[j] = __float2bfloat16_rn(0.5f * bq);
+        }
     }
     sr = warp_sum(sr);
     ss = warp_sum(ss);
@@ -589,6 +635,279 @@ __global__ void k_hlr_finish_step(float* __restrict__ q, float* __restrict__ r, 
     }
 }
 
+__global__ void k_hlr_finish_step(float* __restrict__ q, float* __restrict__ r, const float* __restrict__ part_g,
+                                  int64_t C, int Dx, int D, int n_split, float eps, const float* __restrict__ metric,
+                                  __nv_bfloat16* __restrict__ operand) {
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= C) return;
+    hlr_finish_chain(q + c * D, r + c * D, part_g + c * Dx, C * (int64_t)Dx, Dx, n_split, eps, metric,
+                     operand + c * KJ, lane, false);
+}
+
+// ---- all interior leapfrog steps of a trajectory in ONE persistent launch ----------------------------------------
+// k_hlr_tc<false> + k_hlr_finish_step per leapfrog step are two launches with an ~18 us fixed cost (prologue,
+// pipeline fill, drain, launch gap) around ~45 us of tensor work at c3.  Here the grid (chain tiles x observation
+// slices, one CTA per SM, all co-resident: cooperative launch) stays up for n_steps leapfrog steps.  Per step a CTA
+//   1. streams its observation slice through the same GEMM1 -> residual -> GEMM2 pipeline and writes its partial
+//      gradient [128 chains, Dx] (the X tiles of step s+1 are already prefetched into the ring while step s drains);
+//   2. counts itself in on cnt[s][chain tile][0] and waits until all n_split slices of its chain tile are there;
+//   3. finishes 128 / n_split of the tile's chains (warp per chain, hlr_finish_chain: fixed-order slice sum, prior
+//      terms, kick, drift, next bf16 operand) and counts itself in on cnt[s][chain tile][1];
+//   4. its TMA producer waits for that counter to reach n_split, then loads the new operand (generic-proxy writes of
+//      other CTAs -> async-proxy read: fence.proxy.async on both sides of the release / acquire pair).
+// A chain is always finished by the same warp of the same CTA, so q / r need no cross-CTA ordering; the partials are
+// read with ld.global.cg (they are rewritten every step by other SMs).  Results are bit-identical to the per-step
+// launches (same device function, same summation order).  Waits are bounded (~4 s, then the error word poisons the
+// positions with NaN).
+struct StepsArgs {
+    Args g;
+    float* q;                  // [C, D]
+    float* r;                  // [C, D]
+    int D;
+    float eps;
+    const float* metric;       // [D] or NULL
+    __nv_bfloat16* operand;    // [Cp, 128] beta / 2 of the current q on entry
+    int n_steps;
+    uint32_t* cnt;             // [n_steps][gridDim.x][2], zeroed by the host; then the error word
+    uint32_t* err;
+};
+
+__device__ __forceinline__ void hlr_red_release_add(uint32_t* p, uint32_t v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t hlr_ld_acquire(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *flag >= want; false (and the error word set) after ~4 s or when another waiter already gave up
+__device__ __forceinline__ bool hlr_wait_count(const uint32_t* flag, uint32_t want, uint32_t* err) {
+    if (hlr_ld_acquire(flag) >= want) return true;
+    uint64_t t_start;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
+    unsigned spins = 0;
+    while (hlr_ld_acquire(flag) < want) {
+        __nanosleep(32);
+        if ((++spins & 1023u) == 0) {
+            uint64_t t_now;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_now));
+            if (t_now - t_start > 4000000000ull || *(volatile uint32_t*)err) {
+                atomicExch(err, 1u);
+                return false;
+            }
+        }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(GTHREADS, 1)
+k_hlr_tc_steps(const __grid_constant__ CUtensorMap mapBeta, const __grid_constant__ CUtensorMap mapX,
+               const StepsArgs sa) {
+    extern __shared__ uint8_t smem_raw[];
+    const Args& a = sa.g;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sA1 = base + OFF_A1, sA2 = base + OFF_A2, bars = base + OFF_BARS;
+    auto stage = [&](int s) { return base + OFF_STAGE + (uint32_t)s * STAGE_BYTES; };
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto empty = [&](int s) { return bars + 8u * (NSTAGE + s); };
+    auto d1_full = [&](int b) { return bars + 8u * (2 * NSTAGE + b); };
+    auto a2_full = [&](int b) { return bars + 8u * (2 * NSTAGE + 2 + b); };
+    auto a2_free = [&](int b) { return bars + 8u * (2 * NSTAGE + 4 + b); };
+    const uint32_t d2_full = bars + 8u * (2 * NSTAGE + 6), beta_full = bars + 8u * (2 * NSTAGE + 7),
+                   tmem_slot = bars + 8u * (2 * NSTAGE + 8), d2_free = bars + 8u * (2 * NSTAGE + 9);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(gbase + OFF_BARS + 8 * (2 * NSTAGE + 8));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t c0 = (int64_t)blockIdx.x * CT;
+    const int split = blockIdx.y, n_split = (int)gridDim.y;
+    const int64_t n_begin = split * a.rows_per_split;
+    const int64_t n_end = n_begin + a.rows_per_split < a.N ? n_begin + a.rows_per_split : a.N;
+    const int T = n_end > n_begin ? (int)((n_end - n_begin + NT - 1) / NT) : 0;
+    auto cnt_of = [&](int s) { return sa.cnt + ((int64_t)s * gridDim.x + blockIdx.x) * 2; };
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(d1_full(s), 1); mbar_init(a2_full(s), 16 * EWARPS); mbar_init(a2_free(s), 1); }
+        mbar_init(d2_full, 1); mbar_init(beta_full, 1); mbar_init(d2_free, EWARPS);
+        mbar_init_fence();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot_ptr;
+    const uint32_t tD1 = tmem, tD2 = tmem + 256;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            auto issue_x = [&](int s, int i) {
+                const int gi = s * T + i, sl = gi % NSTAGE;
+                const int n0 = (int)(n_begin + (int64_t)i * NT);
+                mbar_wait(empty(sl), ((uint32_t)(gi / NSTAGE) & 1u) ^ 1u);
+                mbar_expect_tx(full(sl), 2 * ATOM + NT * 4);
+                const uint32_t st = stage(sl);
+                tma_load_2d(st, &mapX, full(sl), 0, n0);
+                tma_load_2d(st + ATOM, &mapX, full(sl), 64, n0);
+                bulk_load(st + 2 * ATOM, a.y + n0, NT * 4, full(sl));
+            };
+            for (int s = 0; s < sa.n_steps; ++s) {
+                // the X tiles do not depend on the step: fill the ring while the previous step drains / finishes
+                const int pre = T < NSTAGE ? T : NSTAGE;
+                for (int i = 0; i < pre; ++i) issue_x(s, i);
+                if (s > 0) {
+                    // every slice of this chain tile has written its rows of the new operand; all MMAs of the
+                    // previous step (the readers of sA1) completed before this CTA counted itself in
+                    hlr_wait_count(cnt_of(s - 1) + 1, (uint32_t)n_split, sa.err);
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
+                if (T > 0) {
+                    mbar_expect_tx(beta_full, 2 * ATOM);
+                    tma_load_2d(sA1, &mapBeta, beta_full, 0, (int)c0);
+                    tma_load_2d(sA1 + ATOM, &mapBeta, beta_full, 64, (int)c0);
+                }
+                for (int i = pre; i < T; ++i) issue_x(s, i);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && T > 0) {
+            auto kdesc = [](uint32_t tile, int kk) { return umma_desc<128>(tile + (kk >> 2) * ATOM + (kk & 3) * 32); };
+            for (int s = 0; s < sa.n_steps; ++s) {
+                auto mma2 = [&](int t) {   // G += R_t . X_t   (A = R in smem, B = the X tile read MN-major)
+                    const int gi = s * T + t, sl = gi % NSTAGE, b = gi & 1;
+                    mbar_wait(a2_full(b), (uint32_t)(gi >> 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t xt = stage(sl), ra = sA2 + (uint32_t)b * 2 * ATOM;
+#pragma unroll
+                    for (int kk = 0; kk < NT / 16; ++kk)
+                        umma(tD2, kdesc(ra, kk), umma_desc_mn128(xt + kk * 2048, ATOM, 1024), IDESC_BMN, (t | kk) != 0);
+                    umma_commit(empty(sl));
+                    umma_commit(a2_free(b));
+                };
+                mbar_wait(beta_full, (uint32_t)s & 1u);
+                if (s > 0) mbar_wait(d2_free, (uint32_t)(s - 1) & 1u);   // the epilogue has read the previous D2
+                tc_fence_after();
+                for (int i = 0; i < T; ++i) {
+                    const int gi = s * T + i, sl = gi % NSTAGE;
+                    mbar_wait(full(sl), (uint32_t)(gi / NSTAGE) & 1u);
+                    tc_fence_after();
+                    const uint32_t d1 = tD1 + (uint32_t)(gi & 1) * 128;
+#pragma unroll
+                    for (int kk = 0; kk < KJ / 16; ++kk) umma(d1, kdesc(sA1, kk), kdesc(stage(sl), kk), IDESC, kk != 0);
+                    umma_commit(d1_full(gi & 1));
+                    if (i >= 1) mma2(i - 1);
+                }
+                mma2(T - 1);
+                umma_commit(d2_full);
+            }
+        }
+    } else {
+        const int ew = warp - 2;                               // epilogue warp 0..15
+        const int quarter = warp & 3, grp = ew >> 3, part = (ew >> 2) & 1;
+        const int part4 = grp * 2 + part;
+        constexpr int PW = NT / 2;
+        const int cl = quarter * 32 + lane;
+        const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+        const uint32_t rrow0 = sA2 + (uint32_t)((part * PW) >> 6) * ATOM + (uint32_t)(cl >> 3) * 1024 +
+                               (uint32_t)(cl & 7) * 128;
+        const int kc0 = ((part * PW) & 63) >> 3;
+        const int64_t c = c0 + cl;
+        const bool elected = threadIdx.x == 64;                // first epilogue thread: the CTA's voice on the counters
+        for (int s = 0; s < sa.n_steps; ++s) {
+            for (int i = 0; i < T; ++i) {
+                const int gi = s * T + i;
+                if ((gi & 1) != grp) continue;                 // the two groups of 8 warps take alternate tiles
+                const int sl = gi % NSTAGE;
+                mbar_wait(full(sl), (uint32_t)(gi / NSTAGE) & 1u);
+                mbar_wait(d1_full(gi & 1), (uint32_t)(gi >> 1) & 1u);
+                tc_fence_after();
+                const float* ys = reinterpret_cast<const float*>(gbase + OFF_STAGE + sl * STAGE_BYTES + 2 * ATOM) + part * PW;
+                const uint32_t d1 = tD1 + (uint32_t)(gi & 1) * 128 + lane_sel + (uint32_t)(part * PW);
+                uint32_t packed[PW / 2];
+#pragma unroll
+                for (int ch = 0; ch < PW / 16; ++ch) {
+                    uint32_t zv[16];
+                    tmem_ld16(d1 + ch * 16, zv);
+#pragma unroll
+                    for (int j4 = 0; j4 < 16; j4 += 4) {
+                        const float4 y4 = *reinterpret_cast<const float4*>(ys + ch * 16 + j4);
+                        const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+                        float rr[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) rr[u] = fmaf(-0.5f, tanh_approx(__uint_as_float(zv[j4 + u])), yv[u]);
+                        __nv_bfloat162 p0 = __floats2bfloat162_rn(rr[0], rr[1]), p1 = __floats2bfloat162_rn(rr[2], rr[3]);
+                        packed[ch * 8 + (j4 >> 1)] = *reinterpret_cast<uint32_t*>(&p0);
+                        packed[ch * 8 + (j4 >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
+                    }
+                }
+                mbar_wait(a2_free(gi & 1), ((uint32_t)(gi >> 1) + 1u) & 1u);
+                const uint32_t rrow = rrow0 + (uint32_t)(gi & 1) * 2 * ATOM;
+#pragma unroll
+                for (int kc = 0; kc < PW / 8; ++kc) {
+                    const uint32_t addr = rrow + (((uint32_t)(kc0 + kc) ^ (uint32_t)(cl & 7)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[4 * kc]),
+                                 "r"(packed[4 * kc + 1]), "r"(packed[4 * kc + 2]), "r"(packed[4 * kc + 3])
+                                 : "memory");
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(a2_full(gi & 1));
+            }
+            // ---- partial gradient of this slice: D2[c, j] -> part_g[split] ----
+            if (T > 0) {
+                mbar_wait(d2_full, (uint32_t)s & 1u);
+                tc_fence_after();
+#pragma unroll 1
+                for (int ch = 0; ch < 2; ++ch) {
+                    uint32_t gv[16];
+                    tmem_ld16(tD2 + lane_sel + (uint32_t)(part4 * 32 + ch * 16), gv);
+                    if (c < a.C) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int jj = part4 * 32 + ch * 16 + j;
+                            if (jj < a.Dx) a.part_g[((int64_t)split * a.C + c) * a.Dx + jj] = __uint_as_float(gv[j]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d2_free);           // D2 may be overwritten by the next step's GEMM2
+            } else if (c < a.C && s == 0) {
+                for (int jj = part4 * 32; jj < part4 * 32 + 32; ++jj)
+                    if (jj < a.Dx) a.part_g[((int64_t)split * a.C + c) * a.Dx + jj] = 0.f;
+            }
+            // ---- all slices of this chain tile in? ----
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EWARPS) : "memory");
+            if (elected) {
+                __threadfence();
+                hlr_red_release_add(cnt_of(s), 1u);
+                hlr_wait_count(cnt_of(s), (uint32_t)n_split, sa.err);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EWARPS) : "memory");
+            // ---- finish + kick + drift + next operand for this CTA's share of the tile's chains ----
+            const bool poison = *(volatile uint32_t*)sa.err != 0u;
+            for (int k = split + n_split * ew; k < CT; k += n_split * EWARPS) {
+                const int64_t cc = c0 + k;
+                if (cc < a.C)
+                    hlr_finish_chain(sa.q + cc * sa.D, sa.r + cc * sa.D, a.part_g + cc * a.Dx, a.C * (int64_t)a.Dx, a.Dx,
+                                     n_split, sa.eps, sa.metric, sa.operand + cc * KJ, lane, poison);
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");   // operand rows: generic-proxy writes -> TMA reads elsewhere
+            __threadfence();
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EWARPS) : "memory");
+            if (elected) hlr_red_release_add(cnt_of(s) + 1, 1u);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
 int hlr_tc_interior_step(const Model& m, float* q, float* r, int64_t C, float eps, const float* metric,
                          bool operand_ready, void* ws, size_t ws_bytes, cudaStream_t st) {
     float *pg, *pl;
@@ -599,6 +918,75 @@ int hlr_tc_interior_step(const Model& m, float* q, float* r, int64_t C, float ep
     const int D = (int)m.d.dims;
     k_hlr_finish_step<<<(unsigned)((C * 32 + 63) / 64), 64, 0, st>>>(q, r, pg, C, D - 2, D, ns, eps, metric, bb);
     BK_LAUNCH_CHECK();
+    return BK_OK;
+}
+
+// n_steps interior leapfrog steps (gradient at q, kick, drift) in persistent launches of up to HLR_MAX_FUSED_STEPS
+// steps each -- only with BK_HLR_FUSE=1: MEASURED SLOWER than the launch pairs (c3: 1.09 vs 0.91 ms per draw,
+// profiles/r2_hlr_fuse_check.log; draws bit-identical).  A leapfrog step is a true dependency chain per chain tile --
+// drain the MMA pipeline, all slices in, finish, operand published, operand reloaded, pipeline refilled -- and with one
+// chain tile per CTA nothing overlaps it; two kernel boundaries cost less than two counter hand-overs plus the finish
+// on the critical path.  Default: one gradient launch + one finish launch per step.
+int hlr_tc_interior_steps(const Model& m, float* q, float* r, int64_t C, float eps, const float* metric, int n_steps,
+                          void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (n_steps <= 0) return BK_OK;
+    static int fuse_env = -1;
+    if (fuse_env < 0) { const char* e = getenv("BK_HLR_FUSE"); fuse_env = (e && e[0] == '1') ? 1 : 0; }
+    const int D = (int)m.d.dims, Dx = D - 2;
+    const int64_t N = m.d.n_obs, Np = pad128(N), Cp = pad128(C);
+    const HlrWs w = hlr_carve(m, C, ws, ws_bytes);
+    if (!w.ok) { set_error("model eval workspace too small (%zu < %zu)", ws_bytes, w.need); return BK_E_WORKSPACE; }
+    // co-residency: one CTA per SM (200 KB of shared memory), the grid must fit the device in one wave
+    static int sms_dev[64] = {0}, occ_dev[64] = {0};
+    int dev = 0;
+    BK_CUDA(cudaGetDevice(&dev));
+    bool fused = fuse_env != 0 && hlr_steps_cnt_words(C) > 0 && dev >= 0 && dev < 64;
+    if (fused && !sms_dev[dev]) {
+        int sms = 0, occ = 0;
+        BK_CUDA(cudaFuncSetAttribute(k_hlr_tc_steps, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_hlr_tc_steps, GTHREADS, SMEM_BYTES) != cudaSuccess) {
+            cudaGetLastError();
+            sms = 1; occ = 0;
+        }
+        sms_dev[dev] = sms; occ_dev[dev] = occ;
+    }
+    if (fused && (Cp / CT) * (int64_t)w.ns > (int64_t)sms_dev[dev] * occ_dev[dev]) fused = false;
+    if (!fused) {
+        for (int s = 0; s < n_steps; ++s) {
+            const int rc = hlr_tc_interior_step(m, q, r, C, eps, metric, s > 0, ws, ws_bytes, st);
+            if (rc) return rc;
+        }
+        return BK_OK;
+    }
+    k_hlr_prep_beta<<<(unsigned)((Cp * KJ + 255) / 256), 256, 0, st>>>(q, C, Cp, Dx, D, 0.5f, w.bb, nullptr);
+    BK_LAUNCH_CHECK();
+    CUtensorMap mB, mX;
+    int rc;
+    if ((rc = make_map_bf16(&mB, w.bb, Cp, KJ, KJ, CT))) return rc;
+    if ((rc = make_map_bf16(&mX, m.Xb, Np, KJ, KJ, NT))) return rc;
+    StepsArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.g.C = C; sa.g.N = N; sa.g.Dx = Dx; sa.g.part_g = w.pg; sa.g.part_ll = w.pl;
+    sa.g.y = m.yh; sa.g.need_ll = 0; sa.g.g_scale = 1.0f; sa.g.debug = 0;
+    const int64_t rows = (N + w.ns - 1) / w.ns;
+    sa.g.rows_per_split = (rows + NT - 1) / NT * NT;
+    sa.q = q; sa.r = r; sa.D = D; sa.eps = eps; sa.metric = metric; sa.operand = w.bb;
+    const size_t cnt_words = hlr_steps_cnt_words(C);
+    sa.cnt = w.cnt; sa.err = w.cnt + (cnt_words - 1);
+    dim3 grid((unsigned)(Cp / CT), (unsigned)w.ns);
+    for (int done = 0; done < n_steps;) {
+        const int ns_now = n_steps - done < HLR_MAX_FUSED_STEPS ? n_steps - done : HLR_MAX_FUSED_STEPS;
+        sa.n_steps = ns_now;
+        BK_CUDA(cudaMemsetAsync(w.cnt, 0, cnt_words * sizeof(uint32_t), st));
+        void* args[3] = {(void*)&mB, (void*)&mX, (void*)&sa};
+        prof_begin(BK_PROF_GRAD, st);
+        // cooperative: every CTA spins on counters the others advance, so the whole grid must be resident
+        BK_CUDA(cudaLaunchCooperativeKernel((const void*)k_hlr_tc_steps, grid, dim3(GTHREADS), args, SMEM_BYTES, st));
+        prof_end(BK_PROF_GRAD, st);
+        count_launch();
+        done += ns_now;
+    }
     return BK_OK;
 }
 

@@ -53,5 +53,8 @@ int hlr_tc_partial(const Model& m, const float* theta, int64_t C, void* ws, size
 // operand_ready: the operand of q was written by the previous call (same ws, same C).
 int hlr_tc_interior_step(const Model& m, float* q, float* r, int64_t C, float eps, const float* metric,
                          bool operand_ready, void* ws, size_t ws_bytes, cudaStream_t st);
+// n_steps of them; one persistent launch when the grid fits the device in one wave (logreg_tc.cu)
+int hlr_tc_interior_steps(const Model& m, float* q, float* r, int64_t C, float eps, const float* metric, int n_steps,
+                          void* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace bk

@@ -291,19 +291,18 @@ int run_generic(const Model& m, GenArgs<T> p, int algo, int* cache_valid, void* 
         if (algo == ALGO_HMC) {
             k_hmc_begin<T><<<blocks, 256, 0, st>>>(p, t);
             BK_LAUNCH_CHECK();
-            bool operand_ready = false;
-            for (int s = 0; s < p.L; ++s) {
-                if constexpr (sizeof(T) == 4) {
-                    // regression plugin, interior step: tensor-core gradient + ONE fused kernel
-                    // (gradient finish, kick, drift, next bf16 operand) -- logreg_tc.cu
-                    if (fast && m.d.kind == BK_MODEL_HIER_LOGREG && s + 1 < p.L) {
-                        rc = hlr_tc_interior_step(m, (float*)p.q, (float*)p.r, p.C, (float)p.eps,
-                                                  (const float*)p.metric, operand_ready, ews, ebytes, st);
-                        if (rc) return rc;
-                        operand_ready = true;
-                        continue;
-                    }
+            int s_first = 0;
+            if constexpr (sizeof(T) == 4) {
+                // regression plugin, interior steps: tensor-core gradient + finish + kick + drift + next bf16
+                // operand, all L - 1 of them in one persistent launch -- logreg_tc.cu
+                if (fast && m.d.kind == BK_MODEL_HIER_LOGREG && p.L > 1) {
+                    rc = hlr_tc_interior_steps(m, (float*)p.q, (float*)p.r, p.C, (float)p.eps,
+                                               (const float*)p.metric, p.L - 1, ews, ebytes, st);
+                    if (rc) return rc;
+                    s_first = p.L - 1;
                 }
+            }
+            for (int s = s_first; s < p.L; ++s) {
                 // Gradients may come from the plugin's reduced-precision tensor-core path at
                 // EVERY step: leapfrog with any deterministic gradient function is reversible
                 // and volume preserving (the endpoint gradient is also what the next

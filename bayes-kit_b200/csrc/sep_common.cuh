@@ -20,13 +20,18 @@ struct SepModel {
     const T* metric;  // [D] or NULL (identity)
 };
 
-template <typename T, int G, int J>
+// VM fixes the row access mode at compile time (hot kernels: no per-block path selection in the instruction stream):
+// -1 = decided at run time by vec / vec2, 0 = scalar, 1 = 128-bit (D % 4 == 0, rows 16-byte aligned), 2 = 64-bit
+// (fp32, D even, rows 8-byte aligned).
+template <typename T, int G, int J, int VM = -1>
 struct Lanes {
     static constexpr int NE = 4 * J;
     int lane;   // lane within group
     int D;
     bool vec;
     bool vec2 = false;   // fp32, D even, rows 8-byte aligned (e.g. D = 50): 64-bit accesses, two per element block
+    __device__ __forceinline__ bool m_vec() const { return VM < 0 ? vec : VM == 1; }
+    __device__ __forceinline__ bool m_vec2() const { return VM < 0 ? (sizeof(T) == 4 && vec2) : (sizeof(T) == 4 && VM == 2); }
     __device__ __forceinline__ int elem(int k) const { return 4 * (lane + G * (k >> 2)) + (k & 3); }
     __device__ __forceinline__ bool valid(int k) const { return elem(k) < D; }
 
@@ -34,7 +39,10 @@ struct Lanes {
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             int e0 = 4 * (lane + G * j);
-            if (vec && e0 + 3 < D) {
+            if (VM == 1 && e0 >= D) {   // D % 4 == 0: a block is all valid or all padding
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[4 * j + i] = fill;
+            } else if (VM == 1 || (m_vec() && e0 + 3 < D)) {
                 if constexpr (sizeof(T) == 4) {
                     float4 t = *reinterpret_cast<const float4*>(row + e0);
                     v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
@@ -43,7 +51,7 @@ struct Lanes {
                     double2 b = *reinterpret_cast<const double2*>(row + e0 + 2);
                     v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = b.x; v[4 * j + 3] = b.y;
                 }
-            } else if (sizeof(T) == 4 && vec2) {
+            } else if (m_vec2()) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     if (e0 + 2 * h + 1 < D) {
@@ -63,7 +71,8 @@ struct Lanes {
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             int e0 = 4 * (lane + G * j);
-            if (vec && e0 + 3 < D) {
+            if (VM == 1 && e0 >= D) {
+            } else if (VM == 1 || (m_vec() && e0 + 3 < D)) {
                 if constexpr (sizeof(T) == 4) {
                     *reinterpret_cast<float4*>(row + e0) =
                         make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -71,7 +80,7 @@ struct Lanes {
                     *reinterpret_cast<double2*>(row + e0) = make_double2(v[4 * j], v[4 * j + 1]);
                     *reinterpret_cast<double2*>(row + e0 + 2) = make_double2(v[4 * j + 2], v[4 * j + 3]);
                 }
-            } else if (sizeof(T) == 4 && vec2) {
+            } else if (m_vec2()) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
                     if (e0 + 2 * h + 1 < D)

@@ -56,7 +56,8 @@ struct GplView {
     using A = Ar<T>;
     static constexpr int NE = 4 * J;
     T mu[NE], pl[NE], m0[NE], p0[NE];
-    __device__ __forceinline__ void init(const SmcArgs<T>& a, const Lanes<T, G, J>& ln) {
+    template <typename LN>
+    __device__ __forceinline__ void init(const SmcArgs<T>& a, const LN& ln) {
         ln.load(a.mu, mu, T(0));
         ln.load(a.pl, pl, T(0));
         ln.load(a.m0, m0, T(0));
@@ -95,7 +96,8 @@ struct BinomView {
     using A = Ar<T>;
     static constexpr int NE = 4 * J;
     T al, be, xs, Nn, lch, lbe;
-    __device__ __forceinline__ void init(const SmcArgs<T>& a, const Lanes<T, G, J>&) {
+    template <typename LN>
+    __device__ __forceinline__ void init(const SmcArgs<T>& a, const LN&) {
         al = a.bp[0]; be = a.bp[1]; xs = a.bp[2]; Nn = a.bp[3]; lch = a.bp[4]; lbe = a.bp[5];
     }
     __device__ __forceinline__ void terms(const T (&x)[NE], T& ll, T& pr) const {
@@ -123,14 +125,17 @@ struct BinomView {
 // resample index and the particle row of the NEXT visit are requested before the current particle is
 // processed (two dependent global loads deep), the accept uniform is drawn by the group's first lane only.
 // MOVE selects the Markov kernel applied at temperature t0 = time(n-1) (smc.py:54-57).
-template <typename T, int G, int J, template <typename, int, int> class View, int MOVE, int OCC = 0>
+// VM: row access mode fixed at compile time (sep_common.cuh) for the hot layout; -1 = run-time flags.  (c4: 20.4 -> 17.8 ms.
+// Measured and dropped: the model's per-dimension parameters in shared memory instead of registers -- the same 17.8 ms
+// at 3 CTAs / SM, and 22.2 / 26.7 ms at 4 / 5 CTAs per SM, where the register cap spills.)
+template <typename T, int G, int J, template <typename, int, int> class View, int MOVE, int OCC = 0, int VM = -1>
 __global__ void __launch_bounds__(128, OCC ? OCC : (J >= 4 && sizeof(T) == 4) ? 3 : (J == 2 && G == 8) ? 5 : 1) k_smc_move_weight(SmcArgs<T> a) {
     using A = Ar<T>;
     constexpr int NE = 4 * J;
     const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / G;
     const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int64_t n_it = (a.M + n_groups - 1) / n_groups;       // same trip count for every lane of a warp
-    Lanes<T, G, J> ln;
+    Lanes<T, G, J, VM> ln;
     ln.lane = threadIdx.x % G;
     ln.D = a.D;
     ln.vec = a.vec != 0;
@@ -333,7 +338,7 @@ static int device_sms() {
     return sms;
 }
 
-template <typename T, int G, int J, template <typename, int, int> class View, int MOVE, int OCC = 0>
+template <typename T, int G, int J, template <typename, int, int> class View, int MOVE, int OCC = 0, int VM = -1>
 static int launch_smc3(const SmcArgs<T>& a, cudaStream_t st) {
     const int64_t per_block = 128 / G;
     const int64_t need = (a.M + per_block - 1) / per_block;
@@ -342,7 +347,7 @@ static int launch_smc3(const SmcArgs<T>& a, cudaStream_t st) {
     static int64_t cap = 0;
     if (!cap) {
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_smc_move_weight<T, G, J, View, MOVE, OCC>, 128, 0) != cudaSuccess || nb < 1) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_smc_move_weight<T, G, J, View, MOVE, OCC, VM>, 128, 0) != cudaSuccess || nb < 1) {
             cudaGetLastError();
             nb = 1;
         }
@@ -350,7 +355,7 @@ static int launch_smc3(const SmcArgs<T>& a, cudaStream_t st) {
     }
     int64_t blocks = need < cap ? need : cap;
     if (blocks > SMC_MAXPART) blocks = SMC_MAXPART;
-    k_smc_move_weight<T, G, J, View, MOVE, OCC><<<(unsigned)blocks, 128, 0, st>>>(a);
+    k_smc_move_weight<T, G, J, View, MOVE, OCC, VM><<<(unsigned)blocks, 128, 0, st>>>(a);
     BK_LAUNCH_CHECK();
     return BK_OK;
 }
@@ -403,6 +408,8 @@ static int smc_dispatch(const Model& m, SmcArgs<T>& a, const bk_smc_kernel& kn, 
             if (occ < 0) { const char* e = getenv("BK_SMC_OCC"); occ = e ? atoi(e) : 0; }
             if (layout == 2 && occ == 2) return launch_smc3<T, 4, 4, GplView, BK_SMC_KERNEL_RW, 2>(a, st);
             if (layout == 2 && occ == 4) return launch_smc3<T, 4, 4, GplView, BK_SMC_KERNEL_RW, 4>(a, st);
+            if (layout == 2 && a.vec) return launch_smc3<T, 4, 4, GplView, BK_SMC_KERNEL_RW, 0, 1>(a, st);
+            if (layout == 2 && a.vec2) return launch_smc3<T, 4, 4, GplView, BK_SMC_KERNEL_RW, 0, 2>(a, st);
             if (layout == 2) return launch_smc3<T, 4, 4, GplView, BK_SMC_KERNEL_RW>(a, st);
             if (layout == 1) return launch_smc3<T, 8, 2, GplView, BK_SMC_KERNEL_RW>(a, st);
         }

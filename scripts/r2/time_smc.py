@@ -20,5 +20,7 @@ for mode in ("systematic", "multinomial"):
         smc.run_steps(2, T)
         e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
+    chk = float(smc.thetas.double().sum())
     print(json.dumps({"M": M, "D": D, "T": T, "mode": mode, "layout": os.environ.get("BK_SMC_LAYOUT", "default"),
+                      "checksum": chk,
                       "ms_total": best, "ms_per_temperature": best / (T - 1), "particle_steps_per_s": M * (T - 1) / best * 1e3}), flush=True)
