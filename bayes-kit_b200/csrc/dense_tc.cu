@@ -263,6 +263,9 @@ struct StepArgs {
     const float* cvec;    // [D] P*mu or NULL
     float* q_prev;        // tile-blocked (STEP: q_{n-1} in, q_{n+1} out)
     float* q_cur;         // tile-blocked (STEP: q_n, read only within a step; the two swap roles every fused step)
+    float* q_out0;        // NULL, or a third tile-blocked array that receives q_{n+1} of the launch's FIRST step, so that
+                          // q_prev (the trajectory's start = the chain state) survives; later steps ping-pong between
+                          // q_cur and q_out0
     __nv_bfloat16* q_hi_next;  // [C, Dp] (STEP): operand written by even fused steps (0, 2, ...)
     __nv_bfloat16* q_hi_cur;   // operand READ by step 0 (mapB0) = written by odd fused steps; multi-step launches only
     __nv_bfloat16* q_lo_next;  // [C, Dp] or NULL: low half of the LAST fused step's operand
@@ -544,6 +547,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
             int pf_ch = 0, pf_step = 0;
             const float* pf_prev = a.q_prev;     // roles swap every fused step
             const float* pf_cur = a.q_cur;
+            float* const q_alt = a.q_out0 ? a.q_out0 : a.q_prev;   // where the first step's q_{n+1} goes
             uint32_t pf_dst = ring + (uint32_t)(row_in * 128 + seg * 16);
             int pf_slot = 0;
             int64_t pf_e = patch0(pf_tile) + (int64_t)row_in * BM + seg * 4;
@@ -564,7 +568,8 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
                         if (pf_tile >= total_tiles) {     // next fused step: same units, q_{n-1} / q_n swapped
                             pf_tile = unit0;
                             ++pf_step;
-                            const float* t = pf_prev; pf_prev = pf_cur; pf_cur = t;
+                            if (pf_step == 1) { pf_prev = a.q_cur; pf_cur = q_alt; }
+                            else { const float* t = pf_prev; pf_prev = pf_cur; pf_cur = t; }
                         }
                         pf_e = patch0(pf_tile) + (int64_t)row_in * BM + seg * 4;
                     }
@@ -580,7 +585,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
             uint32_t sig_k = 0;                                 // tiles handed to the signaller so far
             for (int step = 0; step < n_steps; ++step)
             for (int64_t tile = unit0; tile < total_tiles; tile += unit_stride) {
-                float* const q_out = (step & 1) ? a.q_cur : a.q_prev;            // q_{n+1} replaces q_{n-1}
+                float* const q_out = (step & 1) ? a.q_cur : q_alt;               // q_{n+1} replaces q_{n-1} (first step: q_out0)
                 __nv_bfloat16* const hi_out = (step & 1) ? a.q_hi_cur : a.q_hi_next;
                 __nv_bfloat16* const lo_out = step == n_steps - 1 ? a.q_lo_next : nullptr;
                 const int m_tile = m_tile_of(tile);
@@ -764,6 +769,11 @@ struct HmcTcArgs {
     int32_t* accept;
     int out_lp;                 // 1: report log p(theta) (MALA, mala.py:66) instead of the joint (hmc.py:63)
     const uint32_t* err;        // fused STEP launch gave up waiting (see StepArgs::err): report NaN
+    // draws 2.. of a sample_n call: the chain state lives in TILE-BLOCKED arrays (qs = position, gs = its gradient)
+    // left there by k_hmc_turn_tc; theta / grad (row-major) are only written by the call's last draw
+    const float *qs, *gs;
+    int old_blocked;            // 1: the state before this draw is (qs, gs); 0: (theta, grad)
+    __nv_bfloat16 *nq_hi, *nq_lo;   // turn: operand of the NEXT trajectory's first GEMM
 };
 
 // One warp per chain, lane-strided blocks of 4 elements (the Philox block
@@ -905,6 +915,14 @@ __global__ void __launch_bounds__(256) k_hmc_end_tc(HmcTcArgs p, int64_t t) {
             ld4<true>(p.gq + bo, 0, 4, g);
             st4<VEC>(p.theta + off, e, D, v);
             st4<VEC>(p.grad + off, e, D, g);
+        } else if (p.old_blocked) {
+            // the state moved into the blocked arrays after the call's first draw: theta / grad are stale
+            float g[4];
+            const int64_t bo = blk_index(c, e, p.m_tiles);
+            ld4<true>(p.qs + bo, 0, 4, v);
+            ld4<true>(p.gs + bo, 0, 4, g);
+            st4<VEC>(p.theta + off, e, D, v);
+            st4<VEC>(p.grad + off, e, D, g);
         } else if (dr) {
             ld4<VEC>(p.theta + off, e, D, v);
         }
@@ -914,6 +932,119 @@ __global__ void __launch_bounds__(256) k_hmc_end_tc(HmcTcArgs p, int64_t t) {
         const float lp_old = p.lp[c];
         if (acc) p.lp[c] = lpq;
         if (p.logp) p.logp[t * p.C + c] = p.out_lp ? (acc ? lpq : lp_old) : (acc ? h1 : h0);
+        if (p.accept) p.accept[t * p.C + c] = acc ? 1 : 0;
+    }
+}
+
+// End of draw t AND begin of draw t + 1 in one pass (draws 1 .. n-1 of a sample_n call): the Metropolis decision of
+// k_hmc_end_tc, then -- instead of copying the accepted state out to theta / grad and reading it back -- the next
+// trajectory starts from where the state already is.  Accepted chains keep q_L / g(q_L) in place (the arrays p.q /
+// p.gq become the state arrays of the next draw); rejected chains get their old state copied into those rows (rare).
+// Then the momentum of draw t + 1, H_0, the first kick and drift: q_1 -> p.qm (q_{L-1} is dead by then; same warp,
+// same rows) and the bf16 operand.  DRAM traffic: 12 B (q_L, q_{L-1}, g) + 10 B (draw, q_1, operand) per element
+// against 24 + 18 for end + begin; 0.56-0.60 ms against 0.21 + 0.53 (c2: 2.97 -> 2.78 ms per draw).  Latency-bound like
+// the end kernel (ncu profiles/r2_ncu_hmc_turn.md: long-scoreboard stalls at the first use of each phase's loads, IPC
+// 1.1): a variant that staged a chain's three rows through shared memory with cp.async (12 KB per warp, next chain
+// requested under the second phase or after it) and 3 instead of 4 CTAs per SM all measured within 0.3 % of this one.
+template <bool VEC>
+__global__ void __launch_bounds__(256, 4) k_hmc_turn_tc(HmcTcArgs p, int64_t t, int write_lo) {
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= p.C) return;
+    const int D = p.D;
+    const int64_t off = c * (int64_t)D;
+    float kin = 0.f, dot = 0.f;
+#pragma unroll 2
+    for (int b = lane; 4 * b < D; b += 32) {
+        const int e = 4 * b;
+        float g[4], qm[4], q[4], m[4] = {1.f, 1.f, 1.f, 1.f}, mu[4] = {0.f, 0.f, 0.f, 0.f};
+        const int64_t bo = blk_index(c, e, p.m_tiles);
+        ld4<true>(p.gq + bo, 0, 4, g);
+        ld4<true>(p.qm + bo, 0, 4, qm);
+        ld4<true>(p.q + bo, 0, 4, q);
+        if (p.metric) ld4<VEC>(p.metric, e, D, m);
+        if (p.mu) ld4<VEC>(p.mu, e, D, mu);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (e + i >= D) break;
+            const float rf = fmaf(q[i] - qm[i], p.inv_eps, p.half_eps * (m[i] * g[i]));
+            kin = fmaf(rf, m[i] * rf, kin);
+            dot = fmaf(q[i] - mu[i], g[i], dot);
+        }
+    }
+    kin = warp_sum(kin);
+    dot = warp_sum(dot);
+    const bool lost = p.err && *p.err != 0u;
+    const float lpq = lost ? __int_as_float(0x7fc00000) : 0.5f * dot;
+    const float h1 = lpq - 0.5f * kin, h0 = lost ? lpq : p.h0[c];
+    float u;
+    if (p.rng.mode == BK_RNG_INJECTED)
+        u = reinterpret_cast<const float*>(p.rng.uniforms)[(t * p.C + c) * p.rng.n_uniform];
+    else
+        u = philox_accept_uniform<float>(p.rng.seed, (uint32_t)(p.rng.chain_offset + (uint64_t)c),
+                                         (uint32_t)(p.rng.draw_offset + (uint64_t)t), D);
+    const bool acc = log_u(u) < h1 - h0;
+    float* dr = p.draws ? p.draws + (t * p.C + c) * (int64_t)D : nullptr;
+    float kin0 = 0.f;
+#pragma unroll 2
+    for (int b = lane; 4 * b < D; b += 32) {
+        const int e = 4 * b;
+        const int64_t bo = blk_index(c, e, p.m_tiles);
+        float v[4], g[4], z[4], m[4] = {1.f, 1.f, 1.f, 1.f};
+        if (acc) {
+            ld4<true>(p.q + bo, 0, 4, v);
+            ld4<true>(p.gq + bo, 0, 4, g);
+        } else {
+            if (p.old_blocked) {
+                ld4<true>(p.qs + bo, 0, 4, v);
+                ld4<true>(p.gs + bo, 0, 4, g);
+            } else {
+                ld4<VEC>(p.theta + off, e, D, v);
+                ld4<VEC>(p.grad + off, e, D, g);
+            }
+            st4<true>(p.q + bo, 0, 4, v);      // the state arrays of the next draw hold every chain
+            st4<true>(p.gq + bo, 0, 4, g);
+        }
+        if (dr) st4<VEC>(dr, e, D, v);
+        // ---- begin of draw t + 1 (k_hmc_begin_tc) from the state in registers ----
+        if (p.metric) ld4<VEC>(p.metric, e, D, m);
+        if (p.rng.mode == BK_RNG_INJECTED)
+            ld4<VEC>(reinterpret_cast<const float*>(p.rng.normals) + ((t + 1) * p.C + c) * (int64_t)D, e, D, z);
+        else
+            philox_normal4<float>(p.rng.seed, (uint32_t)b, (uint32_t)(p.rng.chain_offset + (uint64_t)c),
+                                  (uint32_t)(p.rng.draw_offset + (uint64_t)(t + 1)), z);
+        float q1[4];
+        __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (e + i >= D) { z[i] = 0.f; v[i] = 0.f; g[i] = 0.f; }
+            const float mg = m[i] * g[i];
+            kin0 = fmaf(z[i], m[i] * z[i], kin0);
+            float r = z[i] - p.half_eps * mg;    // backward half kick (hmc.py:46)
+            r = r + p.eps * mg;                  // first full kick     (hmc.py:48)
+            q1[i] = v[i] + p.eps * r;
+            hi[i] = __float2bfloat16_rn(q1[i]);
+            lo[i] = __float2bfloat16_rn(q1[i] - __bfloat162float(hi[i]));
+        }
+        st4<true>(p.qm + bo, 0, 4, q1);
+        const int64_t xo = box_index(c, e, p.Dp / BK, BN);
+        st4_bf16<true>(p.nq_hi + xo, 0, 4, hi);
+        if (write_lo) st4_bf16<true>(p.nq_lo + xo, 0, 4, lo);
+    }
+    for (int b = (D + 3) / 4 + lane; 4 * b < p.Dp; b += 32) {   // pad dims of the operand rows stay zero
+        const __nv_bfloat16 zero4[4] = {__float2bfloat16_rn(0.f), __float2bfloat16_rn(0.f), __float2bfloat16_rn(0.f),
+                                        __float2bfloat16_rn(0.f)};
+        const int64_t xo = box_index(c, 4 * b, p.Dp / BK, BN);
+        st4_bf16<true>(p.nq_hi + xo, 0, 4, zero4);
+        if (write_lo) st4_bf16<true>(p.nq_lo + xo, 0, 4, zero4);
+    }
+    kin0 = warp_sum(kin0);
+    if (lane == 0) {
+        const float lp_old = p.lp[c];
+        const float lp_new = acc ? lpq : lp_old;
+        if (acc) p.lp[c] = lpq;
+        p.h0[c] = lp_new - 0.5f * kin0;
+        if (p.logp) p.logp[t * p.C + c] = p.out_lp ? lp_new : (acc ? h1 : h0);
         if (p.accept) p.accept[t * p.C + c] = acc ? 1 : 0;
     }
 }
@@ -1142,9 +1273,10 @@ int dense_tc_prepare(Model& m, void* ws, size_t ws_bytes, cudaStream_t st) {
 size_t dense_tc_hmc_ws_bytes(const Model& m, int64_t C) {
     const size_t n = (size_t)align_up((size_t)C, tc::BN) * m.Dp;   // tile-blocked, padded
     const size_t nb = n;                                           // box-blocked bf16, padded
-    // q, r, gq fp32; h0; q_hi x2, q_lo bf16; eval scratch for the cache refresh
+    // three positions (state / q_{n-1} / q_n rotate) and two gradients (state / endpoint) fp32; h0; q_hi x2, q_lo
+    // bf16; eval scratch for the cache refresh
     const size_t n_tiles = align_up((size_t)C, tc::BN) / tc::BN;
-    return 3 * align_up(n * 4, 256) + align_up((size_t)C * 4, 256) + 3 * align_up(nb * 2, 256) +
+    return 5 * align_up(n * 4, 256) + align_up((size_t)C * 4, 256) + 3 * align_up(nb * 2, 256) +
            align_up(tc::MAX_FUSED_STEPS * n_tiles * 4 + 256, 256) + model_eval_ws_bytes(m, C) + 2048;
 }
 
@@ -1174,8 +1306,11 @@ int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* 
     const size_t n = (size_t)align_up((size_t)C, tc::BN) * m.Dp;   // tile-blocked, padded
     const size_t nb = n;                                           // box-blocked bf16, padded
     Arena ar(ws, ws_bytes);
-    float* qbuf[2] = {ar.take<float>(n), ar.take<float>(n)};   // q_{n-1} / q_n, roles swap every step
-    float* gq = ar.take<float>(n);
+    // Q[x] = the chain state (q_0 of the running trajectory), Q[y] / Q[z] = q_{n-1} / q_n (roles swap every step);
+    // G[ga] = gradient at the state, G[gb] = endpoint gradient.  After every draw but the last the arrays holding
+    // q_L / g(q_L) BECOME the state arrays (k_hmc_turn_tc), so the indices rotate instead of the data moving.
+    float* Q[3] = {ar.take<float>(n), ar.take<float>(n), ar.take<float>(n)};
+    float* G[2] = {ar.take<float>(n), ar.take<float>(n)};
     float* h0 = ar.take<float>(C);
     __nv_bfloat16* qhi[2] = {ar.take<__nv_bfloat16>(nb), ar.take<__nv_bfloat16>(nb)};
     __nv_bfloat16* qlo = ar.take<__nv_bfloat16>(nb);
@@ -1197,7 +1332,7 @@ int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* 
     // epilogue); rows of pad chains only feed output columns nobody reads
     tc::HmcTcArgs h;
     memset(&h, 0, sizeof(h));
-    h.theta = theta; h.lp = lp; h.grad = grad; h.gq = gq; h.h0 = h0;
+    h.theta = theta; h.lp = lp; h.grad = grad; h.h0 = h0;
     h.metric = metric; h.mu = (const float*)m.d.mu; h.C = C; h.D = D; h.Dp = (int)m.Dp; h.L = L;
     h.m_tiles = (int)(m.Dp / tc::BM);
     h.eps = (float)eps; h.half_eps = (float)(0.5 * eps); h.inv_eps = (float)(1.0 / eps); h.rng = *rng;
@@ -1210,20 +1345,27 @@ int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* 
     a.err = err_word;
     a.C = C; a.D = D; a.Dp = (int)m.Dp;
     a.m_tiles = (int)(m.Dp / tc::BM); a.n_tiles = (C + tc::BN - 1) / tc::BN; a.kblocks = (int)(m.Dp / tc::BK);
-    a.eps = (float)eps; a.metric = metric; a.cvec = (const float*)m.Pmu; a.g_out = gq;
+    a.eps = (float)eps; a.metric = metric; a.cvec = (const float*)m.Pmu;
     a.g_blocked = 1;
     { const char* e = getenv("BK_TC_DEBUG"); a.debug = e ? atoi(e) : 0; }
+    static int turn_env = -1;   // BK_TC_TURN=0 (diagnostic): end + begin as two kernels through theta / grad
+    if (turn_env < 0) { const char* e = getenv("BK_TC_TURN"); turn_env = (e && e[0] == '0') ? 0 : 1; }
     const unsigned wblocks = (unsigned)((C * 32 + 255) / 256);
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     const bool vec = D % 4 == 0 && al16(theta) && al16(grad) && al16(metric) && al16(m.d.mu) &&
                      al16(out.draws) && (rng->mode != BK_RNG_INJECTED || al16(rng->normals));
+    int x = 0, y = 1, z = 2, ga = 0, gb = 1;
+    bool state_blocked = false, begun = false;
     for (int64_t t = 0; t < n_draws; ++t) {
-        h.q_hi = qhi[0]; h.q_lo = qlo;
-        h.qm = qbuf[0]; h.q = qbuf[1];              // begin: q_0 = theta -> qm, q_1 -> q
-        if (vec) tc::k_hmc_begin_tc<true><<<wblocks, 256, 0, st>>>(h, t, L == 1 ? 1 : 0);
-        else tc::k_hmc_begin_tc<false><<<wblocks, 256, 0, st>>>(h, t, L == 1 ? 1 : 0);
-        BK_LAUNCH_CHECK();
-        int cur = 0;
+        if (!begun) {
+            h.q_hi = qhi[0]; h.q_lo = qlo;
+            h.qm = Q[x]; h.q = Q[y];                // begin: q_0 = theta -> Q[x], q_1 -> Q[y]
+            if (vec) tc::k_hmc_begin_tc<true><<<wblocks, 256, 0, st>>>(h, t, L == 1 ? 1 : 0);
+            else tc::k_hmc_begin_tc<false><<<wblocks, 256, 0, st>>>(h, t, L == 1 ? 1 : 0);
+            BK_LAUNCH_CHECK();
+        }
+        int cur = 0, iprev = x, icur = y;           // q_{s-1}, q_s
+        bool first = true;
         const int max_fuse = tc::max_fused_steps(a.m_tiles, a.debug);
         for (int s = 1; s < L;) {   // fused gradient + kick + drift, bf16 operands; up to max_fuse steps per launch
             const int ns = (L - s) < max_fuse ? (L - s) : max_fuse;
@@ -1231,23 +1373,50 @@ int dense_tc_hmc(const Model& m, float* theta, float* lp, float* grad, int32_t* 
             a.n_steps = ns; a.sync = sync;
             a.q_hi_next = qhi[cur ^ 1]; a.q_hi_cur = qhi[cur];
             a.q_lo_next = (s + ns == L) ? qlo : nullptr;   // the last step's operand also gets its low half
-            a.q_prev = h.qm; a.q_cur = h.q;         // q_{s+1} overwrites q_{s-1}; roles swap every step
+            a.q_prev = Q[iprev]; a.q_cur = Q[icur];
+            a.q_out0 = first ? Q[z] : nullptr;      // the trajectory's first step leaves the state Q[x] intact
+            a.g_out = nullptr;
             rc = tc::launch_tc(m, a, qhi[cur], nullptr, st);
             if (rc) return rc;
-            if (ns & 1) {
-                cur ^= 1;
-                float* t2 = h.qm; h.qm = h.q; h.q = t2;
+            if (first) {
+                // step 0 wrote Q[z]; later steps ping-pong between Q[y] and Q[z]
+                if (ns & 1) { iprev = y; icur = z; } else { iprev = z; icur = y; }
+                first = false;
+            } else if (ns & 1) {
+                const int t2 = iprev; iprev = icur; icur = t2;
             }
+            if (ns & 1) cur ^= 1;
             s += ns;
         }
         a.n_steps = 1;
         // endpoint gradient with the 3-pass split: enters the Hamiltonian and the cache
-        a.mode = TC_MODE_GRAD; a.n_pass = 3; a.q_hi_next = nullptr; a.q_lo_next = nullptr;
+        a.mode = TC_MODE_GRAD; a.n_pass = 3; a.q_hi_next = nullptr; a.q_lo_next = nullptr; a.q_out0 = nullptr;
+        a.g_out = G[gb];
         rc = tc::launch_tc(m, a, qhi[cur], qlo, st);
         if (rc) return rc;
-        if (vec) tc::k_hmc_end_tc<true><<<wblocks, 256, 0, st>>>(h, t);
-        else tc::k_hmc_end_tc<false><<<wblocks, 256, 0, st>>>(h, t);
-        BK_LAUNCH_CHECK();
+        h.q = Q[icur]; h.qm = Q[iprev]; h.gq = G[gb];
+        h.qs = Q[x]; h.gs = G[ga]; h.old_blocked = state_blocked ? 1 : 0;
+        if (t + 1 < n_draws && turn_env) {
+            // end of draw t + begin of draw t + 1: the arrays holding q_L / g(q_L) become the state arrays
+            h.nq_hi = qhi[0]; h.nq_lo = qlo;
+            if (vec) {
+                tc::k_hmc_turn_tc<true><<<wblocks, 256, 0, st>>>(h, t, L == 1 ? 1 : 0);
+            } else {
+                tc::k_hmc_turn_tc<false><<<wblocks, 256, 0, st>>>(h, t, L == 1 ? 1 : 0);
+            }
+            BK_LAUNCH_CHECK();
+            const int nx = icur, ny = iprev, nz = 3 - icur - iprev;
+            x = nx; y = ny; z = nz;
+            const int tg = ga; ga = gb; gb = tg;
+            state_blocked = true;
+            begun = true;
+        } else {
+            if (vec) tc::k_hmc_end_tc<true><<<wblocks, 256, 0, st>>>(h, t);
+            else tc::k_hmc_end_tc<false><<<wblocks, 256, 0, st>>>(h, t);
+            BK_LAUNCH_CHECK();
+            state_blocked = false;   // theta / grad hold the state again
+            begun = false;
+        }
     }
     return BK_OK;
 }

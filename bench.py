@@ -205,8 +205,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return run_reference_arm(args)
-    for v in ("BK_TC_DEBUG", "BK_DISABLE_TC", "BK_FORCE_GENERIC", "BK_HLR_DEBUG", "BK_ESS", "BK_ACF", "BK_LIB", "BK_TC_FUSE", "BK_TC_PAIR", "BK_SEP_WIDE", "BK_SMC_LAYOUT", "BK_SMC_OCC", "BK_ACF_RFFT"):   # diagnostic switches of the library
-        if os.environ.get(v, "0") not in ("", "0"):
+    for v in ("BK_TC_DEBUG", "BK_DISABLE_TC", "BK_FORCE_GENERIC", "BK_HLR_DEBUG", "BK_ESS", "BK_ACF", "BK_LIB", "BK_TC_FUSE", "BK_TC_PAIR", "BK_SEP_WIDE", "BK_SMC_LAYOUT", "BK_SMC_OCC", "BK_ACF_RFFT", "BK_TC_TURN", "BK_HLR_FUSE", "BK_SEP_LAYOUT"):   # diagnostic switches of the library (for some of them "0" is the diagnostic value)
+        if os.environ.get(v, "") != "":
             raise SystemExit(f"{v} is set: refusing to benchmark a diagnostic configuration")
 
     import numpy as np
@@ -405,10 +405,11 @@ def main():
                 "launches_timed": int(sn.value), "avg_launch_ms": s_avg_ms,
                 "share_of_step": sms_.value / ms if ms else None, "peak_source": peak_src,
                 "whole_step": {  # every kernel of a draw, on the algorithmic bytes of the whole draw:
-                    # 16 B x C x D per interior leapfrog step + begin (18 B) + end (24 B) + GRAD operand/gradient (10 B)
-                    "bytes_per_draw": (16.0 * (L - 1) + 18 + 24 + 10) * C * D,
-                    "achieved": (16.0 * (L - 1) + 18 + 24 + 10) * C * D * n_draws_timed / (ms * 1e-3) / 1e9,
-                    "frac": (16.0 * (L - 1) + 18 + 24 + 10) * C * D * n_draws_timed / (ms * 1e-3) / 1e9 / peak_bw},
+                    # 16 B x C x D per interior leapfrog step + GRAD operand/gradient (10 B) + the row kernels of a
+                    # sample_n(n) call: one begin (18 B), n - 1 turns (end + begin fused, 22 B), one end (24 B)
+                    "bytes_per_draw": (16.0 * (L - 1) + 10 + (18 + 24 + 22 * (n - 1)) / n) * C * D,
+                    "achieved": (16.0 * (L - 1) + 10 + (18 + 24 + 22 * (n - 1)) / n) * C * D * n_draws_timed / (ms * 1e-3) / 1e9,
+                    "frac": (16.0 * (L - 1) + 10 + (18 + 24 + 22 * (n - 1)) / n) * C * D * n_draws_timed / (ms * 1e-3) / 1e9 / peak_bw},
                 "tensor_side": {  # the endpoint gradient (3-pass bf16 split) is tensor-bound
                     "kernel": "k_dense_tc GRAD mode", "flops_per_launch": 3 * 2.0 * C * D * D,
                     "avg_launch_ms": g_avg_ms, "launches_timed": int(gn.value),
