@@ -245,3 +245,44 @@ def test_rwm_smc_binom(bk):      # test_tempered_smc.py:8-30: M = 75, N = 15, me
         means.append(float(p.mean())); vars_.append(float(p.var()))
     assert abs(np.mean(means) - model.posterior_mean()) < 0.05        # the reference's tolerances for ONE run
     assert abs(np.mean(vars_) - model.posterior_variance()) < 0.01
+
+
+# ---- lane layouts and leapfrog forms of the fused isotropic kernel (sampler_sep_kernel.cuh / sampler_sep_narrow.cu) -----
+@pytest.mark.parametrize("D,L,eps", [(70, 9, 0.17), (84, 10, 0.15), (100, 7, 0.2), (108, 1, 0.3), (124, 10, 0.15),
+                                     (50, 10, 0.15), (100, 2, 0.3)])
+def test_hmc_iso_layouts_and_step_parity(bk, D, L, eps):
+    """4 x J narrow layouts (D = 70 / 84 / 100 / 108: J = 5 / 6 / 7 / 7), the power-of-two ones (50, 124), odd and even
+    L (the position-form recurrence ends in either of its two arrays) and L = 1: moments within 4 MCSE."""
+    s = bk.HMCDiag(bk.IsoGauss(D), eps, L, chains=512, seed=11)
+    s.sample_n(60, keep_draws=False)
+    draws, _ = s.sample_n(300)
+    _check_moments(bk, draws, np.zeros(D), np.ones(D))
+    assert 0.7 < float(s.last_accept.float().mean()) <= 1.0
+
+
+def test_hmc_iso_small_stepsize_keeps_the_force(bk):
+    """eps^2 prec < 2^-10: the position-form coefficient 2 - eps^2 prec would round the force away in fp32, so the
+    kernel takes the velocity form.  200 steps of eps = 0.01 must still move and sample N(0, 1)."""
+    D = 100
+    s = bk.HMCDiag(bk.IsoGauss(D), 0.01, 150, chains=512, seed=12)
+    s.sample_n(20, keep_draws=False)
+    draws, _ = s.sample_n(150)
+    _check_moments(bk, draws, np.zeros(D), np.ones(D))
+    assert float(s.last_accept.float().mean()) > 0.99
+
+
+def test_hmc_iso_zero_steps_stays_put(bk):
+    """hmc.py:43-44: with steps = 0 the two half kicks cancel and the proposal is the current point."""
+    th0 = torch.randn(64, 100)
+    s = bk.HMCDiag(bk.IsoGauss(100), 0.1, 0, init=th0, seed=13)
+    d, _ = s.sample_n(3)
+    assert torch.equal(d[-1].cpu(), th0.to(d.dtype))
+
+
+@pytest.mark.parametrize("D", [70, 100, 108])
+def test_mala_metropolis_narrow_layouts(bk, D):
+    for s, n in ((bk.MALA(bk.IsoGauss(D), 0.05, chains=512, seed=14), 600),
+                 (bk.Metropolis(bk.IsoGauss(D), bk.GaussianRW(0.25), chains=512, seed=15), 2500)):
+        s.sample_n(n // 2, keep_draws=False)
+        draws, _ = s.sample_n(n)
+        _check_moments(bk, draws, np.zeros(D), np.ones(D))

@@ -114,11 +114,12 @@ def test_sharded_smc_adaptive(bk, world):
     np.testing.assert_allclose(np.concatenate([np_(s.log_weights) for s in ranks]), ologw, rtol=1e-10, atol=1e-12)
 
 
-@pytest.mark.parametrize("world", [2, 8])
-def test_sharded_smc_philox_invariant(bk, world):
+@pytest.mark.parametrize("world,D", [(2, 50), (8, 50), (3, 52), (2, 45)])
+def test_sharded_smc_philox_invariant(bk, world, D):
     """fp32 device-RNG mode: the particles after T temperatures do not depend on the number of ranks
-    (Philox is keyed by the global particle id, the fixed-point CDF is exact)."""
-    D, M, T = 50, 20000, 8
+    (Philox is keyed by the global particle id, the fixed-point CDF is exact).  D = 50 / 52 / 45: the move kernel's
+    64-bit, 128-bit (compile-time row access modes) and run-time row access paths."""
+    M, T = 20000, 8
     g = torch.Generator(device="cuda").manual_seed(1)
     mu = torch.randn(D, device="cuda", generator=g)
     th0 = torch.randn(M, D, device="cuda", generator=g)
