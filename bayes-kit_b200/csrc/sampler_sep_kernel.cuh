@@ -111,15 +111,7 @@ __global__ void __launch_bounds__(128) k_sep_sampler(SepArgs<T> a) {
             } else {
                 T xa[NE], xb[NE];
 #pragma unroll
-                for (int k = 0; k < NE; ++k) { xa[k] = th[k]; xb[k] = fmaf(a.eps, z[k], hc * th[k]); }
-                int s = 1;
-                for (; s + 1 < a.L; s += 2) {
-#pragma unroll
-                    for (int k = 0; k < NE; ++k) {
-                        xa[k] = fmaf(c, xb[k], -xa[k]);
-                        xb[k] = fmaf(c, xa[k], -xb[k]);
-                    }
-                }
+                for (int k = 0; k < NE; ++k) xb[k] = fmaf(a.eps, z[k], hc * th[k]);   // x_1
                 auto finish = [&](const T (&cur)[NE], const T (&prev)[NE]) {
                     T s1 = T(0), se = T(0);
 #pragma unroll
@@ -136,12 +128,27 @@ __global__ void __launch_bounds__(128) k_sep_sampler(SepArgs<T> a) {
                     }
                     out_lp = acc ? h1 : h0;
                 };
-                if (s < a.L) {   // odd number of recurrence steps left: x_L lands in xa
-#pragma unroll
-                    for (int k = 0; k < NE; ++k) xa[k] = fmaf(c, xb[k], -xa[k]);
-                    finish(xa, xb);
+                if (a.L == 1) {
+                    finish(xb, th);
                 } else {
-                    finish(xb, xa);
+                    // x_s in xa, x_{s-1} in xb (no copy of the state: the first recurrence step reads th itself)
+#pragma unroll
+                    for (int k = 0; k < NE; ++k) xa[k] = fmaf(c, xb[k], -th[k]);   // x_2
+                    int s = 2;
+                    for (; s + 1 < a.L; s += 2) {
+#pragma unroll
+                        for (int k = 0; k < NE; ++k) {
+                            xb[k] = fmaf(c, xa[k], -xb[k]);
+                            xa[k] = fmaf(c, xb[k], -xa[k]);
+                        }
+                    }
+                    if (s < a.L) {   // one recurrence step left: x_L lands in xb
+#pragma unroll
+                        for (int k = 0; k < NE; ++k) xb[k] = fmaf(c, xa[k], -xb[k]);
+                        finish(xb, xa);
+                    } else {
+                        finish(xa, xb);
+                    }
                 }
             }
         } else if constexpr (ALGO == ALGO_HMC) {

@@ -109,8 +109,13 @@ struct Lanes {
                 uint32_t w[2];
                 philox_normal4<T>(rng.seed, (uint32_t)blk, gc, gd, q, w);
                 if (raw2 && blk == ub) { raw2[0] = w[0]; raw2[1] = w[1]; }
+                if (4 * G * (j + 1) <= D) {   // warp-uniform: block j of EVERY lane is real -> no per-element masks
 #pragma unroll
-                for (int i = 0; i < 4; ++i) z[4 * j + i] = (4 * blk + i < D) ? q[i] : T(0);
+                    for (int i = 0; i < 4; ++i) z[4 * j + i] = q[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) z[4 * j + i] = (4 * blk + i < D) ? q[i] : T(0);
+                }
             }
         }
     }
