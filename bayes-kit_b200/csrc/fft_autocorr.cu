@@ -328,40 +328,83 @@ struct RfTw {
     }
 };
 
-// one in-place radix-R pass over the M-point line in shared memory; block length n = R m (see radix_pass)
-template <int R, bool INV, class Load, class Store>
-__device__ __forceinline__ void rf_pass(int M, int m, const RfTw& tw, Load ld, Store st) {
+// w^1 .. w^(R-1) from w^1 by a product tree of depth log2 R (w^k = w^hb w^(k-hb), hb = the highest power of two in k;
+// squares for the powers of two): R - 2 complex multiplies, no table look-ups and no index arithmetic per twiddle,
+// and no serial chain (a running product w^k = w^(k-1) w would be one).
+__host__ __device__ constexpr int rf_hb(int k) { int h = 1; while (2 * h <= k) h *= 2; return h; }
+template <int R>
+__device__ __forceinline__ void rf_powers(cplx (&w)[R]) {
+#pragma unroll
+    for (int k = 2; k < R; ++k) {
+        const int h = rf_hb(k);
+        if (k == h) {
+            const cplx b = w[k / 2];
+            w[k] = cplx{fma(b.x, b.x, -b.y * b.y), 2.0 * b.x * b.y};
+        } else {
+            w[k] = cmul(w[h], w[k - h]);
+        }
+    }
+}
+
+// one in-place radix-R pass over the M-point line in shared memory; block length n = R m (see radix_pass).
+// LIN: the R elements of a butterfly sit at a constant stride in the SKEWED line (element i lives at i + i / 8):
+// for m % 8 == 0, SK(base + j m) = SK(base) + j (m + m / 8); for R m <= 8 a butterfly stays inside one group of 8.
+// GL / GS: the load / store side goes through the callback (first forward pass reads the series, last inverse pass
+// writes the lags) instead of the line.
+template <int R, bool INV, bool LIN, bool GL, bool GS, class Load, class Store>
+__device__ __forceinline__ void rf_pass(cplx* __restrict__ buf, int M, int m, const RfTw& tw, Load ld, Store st) {
     const int cnt = M / R, n = R * m, tw_stride = M / n;
     const int log2m = 31 - __clz(m);            // m is a power of two in every pass (the odd factor goes first)
+    const int es = m >= 8 ? m + (m >> 3) : m;   // element stride in the skewed line (LIN)
     for (int t = threadIdx.x; t < cnt; t += RF_THREADS) {
         const int p = t & (m - 1), base = (t >> log2m) * n + p;
-        const int q = p * tw_stride;            // w_n^(p k) = w_M^(k q), k q < M for every k < R
+        cplx* pb = buf + base + (base >> 3);
         cplx a[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-            a[j] = ld(base + j * m);
-            if (INV && j > 0) a[j] = cmul(a[j], tw.at(j * q, true));
+            if constexpr (GL) a[j] = ld(base + j * m);
+            else if constexpr (LIN) a[j] = pb[j * es];
+            else { const int i = base + j * m; a[j] = buf[i + (i >> 3)]; }
+        }
+        cplx w[R];
+        w[1] = tw.at(p * tw_stride, INV);       // w_n^p = w_M^(p M / n); the other twiddles are its powers
+        rf_powers<R>(w);
+        if constexpr (INV) {
+#pragma unroll
+            for (int j = 1; j < R; ++j) a[j] = cmul(a[j], w[j]);
         }
         dft_small<R, INV>(a);
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             cplx v = a[out_slot<R>(k)];
-            if (!INV && k > 0) v = cmul(v, tw.at(k * q, false));
-            st(base + k * m, v);
+            if (!INV && k > 0) v = cmul(v, w[k]);
+            if constexpr (GS) st(base + k * m, v);
+            else if constexpr (LIN) pb[k * es] = v;
+            else { const int i = base + k * m; buf[i + (i >> 3)] = v; }
         }
     }
     __syncthreads();
 }
-template <bool INV, class Load, class Store>
-__device__ __forceinline__ void rf_pass_r(int R, int M, int m, const RfTw& tw, Load ld, Store st) {
+template <bool INV, bool GL, bool GS, class Load, class Store>
+__device__ __forceinline__ void rf_pass_r(int R, cplx* __restrict__ buf, int M, int m, const RfTw& tw, Load ld, Store st) {
+    const bool lin = m >= 8 || R * m <= 8;
+#define BK_RF_CASE(RR)                                                                     \
+    case RR:                                                                               \
+        if (lin) rf_pass<RR, INV, true, GL, GS>(buf, M, m, tw, ld, st);                    \
+        else rf_pass<RR, INV, false, GL, GS>(buf, M, m, tw, ld, st);                       \
+        break;
     switch (R) {
-        case 16: rf_pass<16, INV>(M, m, tw, ld, st); break;
-        case 8: rf_pass<8, INV>(M, m, tw, ld, st); break;
-        case 5: rf_pass<5, INV>(M, m, tw, ld, st); break;
-        case 4: rf_pass<4, INV>(M, m, tw, ld, st); break;
-        case 3: rf_pass<3, INV>(M, m, tw, ld, st); break;
-        default: rf_pass<2, INV>(M, m, tw, ld, st); break;
+        BK_RF_CASE(16)
+        BK_RF_CASE(8)
+        BK_RF_CASE(5)
+        BK_RF_CASE(4)
+        BK_RF_CASE(3)
+        default:
+            if (lin) rf_pass<2, INV, true, GL, GS>(buf, M, m, tw, ld, st);
+            else rf_pass<2, INV, false, GL, GS>(buf, M, m, tw, ld, st);
+            break;
     }
+#undef BK_RF_CASE
 }
 // position of frequency k after the forward passes (mixed-radix digit reversal)
 __device__ __forceinline__ int rf_pos(const RfftPlan& pl, int k) {
@@ -381,8 +424,12 @@ __device__ __forceinline__ int rf_pos(const RfftPlan& pl, int k) {
     return i;
 }
 
+// TIN = element type of the draws; the per-series base offset (a 64-bit division / modulo in SeriesView::at) is
+// formed once per series, the draw stride is 32-bit.
+template <typename TIN>
 __global__ void __launch_bounds__(RF_THREADS, 1)
-k_acf_rfft(SeriesView v, RfftPlan plan, const cplx* __restrict__ WM, const cplx* __restrict__ WS, double* __restrict__ out) {
+k_acf_rfft(SeriesView v, RfftPlan plan, const cplx* __restrict__ WM, const cplx* __restrict__ WS,
+           const uint16_t* __restrict__ POS, double* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char rf_smem[];
     cplx* buf = reinterpret_cast<cplx*>(rf_smem);          // [M]
     __shared__ double red[33];
@@ -392,7 +439,8 @@ k_acf_rfft(SeriesView v, RfftPlan plan, const cplx* __restrict__ WM, const cplx*
     for (int j = threadIdx.x; j < RF_TW_LO; j += RF_THREADS) tw_lo[j] = WM[j < M ? j : 0];
     __syncthreads();
     const RfTw WMt{tw_hi, tw_lo};
-    const int64_t N = v.N;
+    const int N = (int)v.N;
+    const int ds = (int)v.dstride;
     // element i lives at i + i / 8: the butterflies of the late passes walk the line with strides of 8 and 128
     // elements (16 B each) -- unskewed that is a 32-way / 4-way bank conflict, skewed every access pattern of the
     // transform costs the minimum of four wavefronts per 512-byte warp request
@@ -400,26 +448,37 @@ k_acf_rfft(SeriesView v, RfftPlan plan, const cplx* __restrict__ WM, const cplx*
     auto ld_buf = [&](int i) { return buf[SK(i)]; };
     auto st_buf = [&](int i, cplx val) { buf[SK(i)] = val; };
     for (int64_t s = blockIdx.x; s < v.n_series; s += gridDim.x) {
+        const TIN* __restrict__ xs = reinterpret_cast<const TIN*>(v.x) + (s / v.n_inner) * v.ostride + (s % v.n_inner) * v.istride;
+        double* __restrict__ os = out + s * (int64_t)N;
         double l1 = 0;
-        for (int64_t t = threadIdx.x; t < N; t += RF_THREADS) l1 += v.at(s, t);
+        for (int t = threadIdx.x; t < N; t += RF_THREADS) l1 += (double)xs[(int64_t)t * ds];
+        // the NEXT series of this CTA: pull its lines into L2 now, its mean pass and packed load start one transform later
+        if (ds == 1 && s + gridDim.x < v.n_series) {
+            const int64_t s2 = s + gridDim.x;
+            const char* nx = reinterpret_cast<const char*>(reinterpret_cast<const TIN*>(v.x) + (s2 / v.n_inner) * v.ostride +
+                                                           (s2 % v.n_inner) * v.istride);
+            for (int64_t b = (int64_t)threadIdx.x * 128; b < (int64_t)N * (int64_t)sizeof(TIN); b += (int64_t)RF_THREADS * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + b));
+        }
         const double mean = block_sum(l1, red) / (double)N;
         // ---- forward: packed load (even + i odd, demeaned, zero padded) fused into the first pass ----
         for (int ps = 0; ps < plan.n_pass; ++ps) {
             if (ps == 0) {
                 auto ld = [&](int i) {
-                    const int64_t e = 2 * (int64_t)i;
-                    return cplx{e < N ? v.at(s, e) - mean : 0.0, e + 1 < N ? v.at(s, e + 1) - mean : 0.0};
+                    const int e = 2 * i;
+                    return cplx{e < N ? (double)xs[(int64_t)e * ds] - mean : 0.0,
+                                e + 1 < N ? (double)xs[(int64_t)(e + 1) * ds] - mean : 0.0};
                 };
-                rf_pass_r<false>(plan.radix[ps], M, plan.m[ps], WMt, ld, st_buf);
+                rf_pass_r<false, true, false>(plan.radix[ps], buf, M, plan.m[ps], WMt, ld, st_buf);
             } else {
-                rf_pass_r<false>(plan.radix[ps], M, plan.m[ps], WMt, ld_buf, st_buf);
+                rf_pass_r<false, false, false>(plan.radix[ps], buf, M, plan.m[ps], WMt, ld_buf, st_buf);
             }
         }
         // ---- pointwise: power spectrum of the real series -> packed spectrum of its autocorrelation ----
         double r0 = 0;
         for (int k = threadIdx.x; k <= M / 2; k += RF_THREADS) {
-            const int k2 = (M - k) % M;                    // partner (k = 0 pairs with itself and carries X[M])
-            const int i = SK(rf_pos(plan, k)), i2 = SK(rf_pos(plan, k2));
+            const int k2 = k ? M - k : 0;                  // partner (k = 0 pairs with itself and carries X[M])
+            const int i = POS[k], i2 = POS[k2];     // skewed positions of the two frequencies (digit reversal: table)
             const cplx a = buf[i], b = buf[i2];
             if (k == 0) {
                 const double x0 = 2.0 * (a.x + a.y), xm = 2.0 * (a.x - a.y);   // X[0] = E + O, X[M] = E - O (real; x2 like the k > 0 terms)
@@ -452,21 +511,23 @@ k_acf_rfft(SeriesView v, RfftPlan plan, const cplx* __restrict__ WM, const cplx*
         for (int ps = plan.n_pass - 1; ps >= 0; --ps) {
             if (ps == 0) {
                 auto st_out = [&](int i, cplx val) {
-                    const int64_t e = 2 * (int64_t)i;
-                    if (e < N) out[s * N + e] = val.x * sc;
-                    if (e + 1 < N) out[s * N + e + 1] = val.y * sc;
+                    const int e = 2 * i;
+                    if (e < N) os[e] = val.x * sc;
+                    if (e + 1 < N) os[e + 1] = val.y * sc;
                 };
-                rf_pass_r<true>(plan.radix[ps], M, plan.m[ps], WMt, ld_buf, st_out);
+                rf_pass_r<true, false, true>(plan.radix[ps], buf, M, plan.m[ps], WMt, ld_buf, st_out);
             } else {
-                rf_pass_r<true>(plan.radix[ps], M, plan.m[ps], WMt, ld_buf, st_buf);
+                rf_pass_r<true, false, false>(plan.radix[ps], buf, M, plan.m[ps], WMt, ld_buf, st_buf);
             }
         }
     }
 }
 
 // WM[j] = exp(-2 pi i j / M) (j < M), WS[k] = exp(-2 pi i k / (2 M)) (k <= M / 2)
-__global__ void k_rfft_twiddles(cplx* __restrict__ WM, cplx* __restrict__ WS, int M) {
+// POS[k] = skewed position of frequency k after the forward passes (k < M)
+__global__ void k_rfft_twiddles(cplx* __restrict__ WM, cplx* __restrict__ WS, uint16_t* __restrict__ POS, RfftPlan plan, int M) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < M) { const int i = rf_pos(plan, j); POS[j] = (uint16_t)(i + (i >> 3)); }
     double sn, cs;
     if (j < M) {
         sincospi(-2.0 * (double)j / (double)M, &sn, &cs);
@@ -537,32 +598,38 @@ static bool use_rfft(int64_t N) {
 size_t acf_fft_ws_bytes(int64_t n_series, int64_t N) {
     if (use_rfft(N)) {
         const int64_t M = rfft_size(N) / 2;
-        return align_up((size_t)M * sizeof(cplx), 256) + align_up((size_t)(M / 2 + 1) * sizeof(cplx), 256) + 512;
+        return align_up((size_t)M * sizeof(cplx), 256) + align_up((size_t)(M / 2 + 1) * sizeof(cplx), 256) +
+               align_up((size_t)M * sizeof(uint16_t), 256) + 512;
     }
     const int64_t S = fft_size(N);
     return align_up((size_t)S * sizeof(cplx), 256) + (size_t)fft_blocks(n_series) * S * sizeof(cplx) + 512;
 }
 
 int acf_fft_launch(const SeriesView& v, double* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    BK_CHECK_ARG(v.dstride < ((int64_t)1 << 31), "bk_autocorr: draw stride %lld too large", (long long)v.dstride);
     if (use_rfft(v.N)) {
         const int M = (int)(rfft_size(v.N) / 2);
         Arena ar(ws, ws_bytes);
         cplx* WM = ar.take<cplx>((size_t)M);
         cplx* WS = ar.take<cplx>((size_t)(M / 2 + 1));
+        uint16_t* POS = ar.take<uint16_t>((size_t)M);
         if (!ar.ok()) {
             set_error("bk_autocorr: workspace too small (need %zu bytes, got %zu)", ar.off, ws_bytes);
             return BK_E_WORKSPACE;
         }
-        k_rfft_twiddles<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(WM, WS, M);
+        const RfftPlan plan = rfft_plan(M);
+        k_rfft_twiddles<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(WM, WS, POS, plan, M);
         BK_LAUNCH_CHECK();
         const size_t smem = (size_t)(M + M / 8 + 1) * sizeof(cplx);
-        BK_CUDA(cudaFuncSetAttribute(k_acf_rfft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BK_CUDA(cudaFuncSetAttribute(k_acf_rfft<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BK_CUDA(cudaFuncSetAttribute(k_acf_rfft<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int per_sm = smem <= 100 * 1024 ? 2 : 1;
         const int64_t nb = v.n_series < (int64_t)sms * per_sm ? v.n_series : (int64_t)sms * per_sm;
-        k_acf_rfft<<<(unsigned)nb, RF_THREADS, smem, st>>>(v, rfft_plan(M), WM, WS, out);
+        if (v.dtype == BK_F64) k_acf_rfft<double><<<(unsigned)nb, RF_THREADS, smem, st>>>(v, plan, WM, WS, POS, out);
+        else k_acf_rfft<float><<<(unsigned)nb, RF_THREADS, smem, st>>>(v, plan, WM, WS, POS, out);
         BK_LAUNCH_CHECK();
         return BK_OK;
     }
