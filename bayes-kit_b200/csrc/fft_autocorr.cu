@@ -476,6 +476,7 @@ k_acf_rfft(SeriesView v, RfftPlan plan, const cplx* __restrict__ WM, const cplx*
         }
         // ---- pointwise: power spectrum of the real series -> packed spectrum of its autocorrelation ----
         double r0 = 0;
+#pragma unroll 4
         for (int k = threadIdx.x; k <= M / 2; k += RF_THREADS) {
             const int k2 = k ? M - k : 0;                  // partner (k = 0 pairs with itself and carries X[M])
             const int i = POS[k], i2 = POS[k2];     // skewed positions of the two frequencies (digit reversal: table)
