@@ -41,6 +41,10 @@ constexpr int OFF_A1 = 0, OFF_STAGE = 2 * ATOM, OFF_A2 = OFF_STAGE + NSTAGE * ST
 constexpr int OFF_BARS = OFF_A2 + 4 * ATOM, OFF_LL = OFF_BARS + 256;   // R is double-buffered
 constexpr int THREADS = 320;                          // k_hlr_lp_tc: 8 epilogue warps
 constexpr int EWARPS = 16, EPARTS = EWARPS / 4;       // k_hlr_tc: 16 epilogue warps (4 observation parts)
+#ifndef BK_HLR_EP_ALL
+#define BK_HLR_EP_ALL 1
+#endif
+constexpr bool EP_ALL = BK_HLR_EP_ALL != 0;           // every epilogue warp on every tile (vs two groups on alternate tiles)
 constexpr int GTHREADS = 64 + 32 * EWARPS;
 constexpr int SMEM_BYTES = OFF_LL + EPARTS * CT * 4 + 1024;
 constexpr uint32_t IDESC = idesc_bf16(128, 128);
@@ -103,7 +107,7 @@ k_hlr_tc(const __grid_constant__ CUtensorMap mapBeta, const __grid_constant__ CU
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(d1_full(s), 1); mbar_init(a2_full(s), 16 * EWARPS); mbar_init(a2_free(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(d1_full(s), 1); mbar_init(a2_full(s), (EP_ALL ? 32 : 16) * EWARPS); mbar_init(a2_free(s), 1); }
         mbar_init(d2_full, 1); mbar_init(beta_full, 1);
         mbar_init_fence();
     }
@@ -164,9 +168,13 @@ k_hlr_tc(const __grid_constant__ CUtensorMap mapBeta, const __grid_constant__ CU
         // buffer g), so the fixed latencies of a tile's hand-offs (TMEM load, proxy fence, mbarrier round
         // trips) overlap with the other group's tile.  TMEM lane quarter = warp % 4 (hardware rule),
         // observation half = bit 2 of (warp - 2).
-        const int quarter = warp & 3, grp = (warp - 2) >> 3, part = ((warp - 2) >> 2) & 1;
-        const int part4 = grp * 2 + part;                      // 0..3: slice of the final gradient read
-        constexpr int PW = NT / 2;                             // observations per thread per tile (64)
+        // EP_ALL (default): all 16 warps work on EVERY tile, 32 observations per thread -- the hand-over latency of a
+        // tile (d1_full -> residuals in shared memory -> a2_full) halves and stays below the 0.9 us the tensor pipe
+        // has queued behind it (GEMM2 of the previous tile + GEMM1 of the next).  !EP_ALL: the r1 arrangement.
+        const int quarter = warp & 3;
+        const int grp = EP_ALL ? 0 : (warp - 2) >> 3, part = EP_ALL ? (warp - 2) >> 2 : ((warp - 2) >> 2) & 1;
+        const int part4 = EP_ALL ? part : grp * 2 + part;      // 0..3: slice of the final gradient read
+        constexpr int PW = EP_ALL ? NT / 4 : NT / 2;           // observations per thread per tile (32 / 64)
         const int cl = quarter * 32 + lane;                    // chain within the tile = TMEM lane
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
         // this chain's row of R: PW k's = PW/8 16-byte chunks, inside atom (part * PW) / 64
@@ -174,7 +182,7 @@ k_hlr_tc(const __grid_constant__ CUtensorMap mapBeta, const __grid_constant__ CU
                                (uint32_t)(cl & 7) * 128;
         const int kc0 = ((part * PW) & 63) >> 3;
         float ll = 0.f;
-        for (int i = grp; i < T; i += 2) {
+        for (int i = grp; i < T; i += EP_ALL ? 1 : 2) {
             const int64_t n0 = n_begin + (int64_t)i * NT;
             mbar_wait(full(i % NSTAGE), (uint32_t)(i / NSTAGE) & 1u);   // acquire the TMA-written y tile
             mbar_wait(d1_full(i & 1), (uint32_t)(i >> 1) & 1u);
