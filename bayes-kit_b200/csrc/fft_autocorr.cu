@@ -429,14 +429,24 @@ __device__ __forceinline__ int rf_pos(const RfftPlan& pl, int k) {
 template <typename TIN>
 __global__ void __launch_bounds__(RF_THREADS, 1)
 k_acf_rfft(SeriesView v, RfftPlan plan, const cplx* __restrict__ WM, const cplx* __restrict__ WS,
-           const uint16_t* __restrict__ POS, double* __restrict__ out) {
+           const uint16_t* __restrict__ POS_g, int pos_in_smem, double* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char rf_smem[];
-    cplx* buf = reinterpret_cast<cplx*>(rf_smem);          // [M]
+    cplx* buf = reinterpret_cast<cplx*>(rf_smem);          // [M + M / 8 + 1] skewed line
     __shared__ double red[33];
     __shared__ cplx tw_hi[RF_TW_HI_MAX], tw_lo[RF_TW_LO];
-    const int M = plan.M;
+    __shared__ int s_rad[6], s_m[6];                       // the plan, out of local memory (it is indexed by the pass)
+    const int M = plan.M, n_pass = plan.n_pass;
     for (int j = threadIdx.x; j * RF_TW_LO < M; j += RF_THREADS) tw_hi[j] = WM[j * RF_TW_LO];
     for (int j = threadIdx.x; j < RF_TW_LO; j += RF_THREADS) tw_lo[j] = WM[j < M ? j : 0];
+    if (threadIdx.x < 6) { s_rad[threadIdx.x] = plan.radix[threadIdx.x]; s_m[threadIdx.x] = plan.m[threadIdx.x]; }
+    // digit-reversed (skewed) positions of the pointwise pass: in shared memory behind the line when they fit
+    const uint16_t* POS = POS_g;
+    if (pos_in_smem) {
+        uint16_t* ps = reinterpret_cast<uint16_t*>(rf_smem + (size_t)(M + M / 8 + 1) * sizeof(cplx));
+        for (int j = threadIdx.x; j < M; j += RF_THREADS) ps[j] = POS_g[j];
+        POS = ps;
+    }
+    const cplx w_s1 = WS[1];                               // exp(-2 pi i / S), S = 2 M
     __syncthreads();
     const RfTw WMt{tw_hi, tw_lo};
     const int N = (int)v.N;
@@ -450,8 +460,15 @@ k_acf_rfft(SeriesView v, RfftPlan plan, const cplx* __restrict__ WM, const cplx*
     for (int64_t s = blockIdx.x; s < v.n_series; s += gridDim.x) {
         const TIN* __restrict__ xs = reinterpret_cast<const TIN*>(v.x) + (s / v.n_inner) * v.ostride + (s % v.n_inner) * v.istride;
         double* __restrict__ os = out + s * (int64_t)N;
+        // ONE pass over the draws: the sum for the mean, and the raw samples parked in the (free) line, packed
+        // z_n = d_2n + i d_2n+1 -- the first forward pass reads them from shared memory and demeans on the fly
         double l1 = 0;
-        for (int t = threadIdx.x; t < N; t += RF_THREADS) l1 += (double)xs[(int64_t)t * ds];
+        double* lined = reinterpret_cast<double*>(buf);
+        for (int t = threadIdx.x; t < N; t += RF_THREADS) {
+            const double xv = (double)xs[(int64_t)t * ds];
+            l1 += xv;
+            lined[2 * SK(t >> 1) + (t & 1)] = xv;
+        }
         // the NEXT series of this CTA: pull its lines into L2 now, its mean pass and packed load start one transform later
         if (ds == 1 && s + gridDim.x < v.n_series) {
             const int64_t s2 = s + gridDim.x;
@@ -462,16 +479,16 @@ k_acf_rfft(SeriesView v, RfftPlan plan, const cplx* __restrict__ WM, const cplx*
         }
         const double mean = block_sum(l1, red) / (double)N;
         // ---- forward: packed load (even + i odd, demeaned, zero padded) fused into the first pass ----
-        for (int ps = 0; ps < plan.n_pass; ++ps) {
+        for (int ps = 0; ps < n_pass; ++ps) {
             if (ps == 0) {
-                auto ld = [&](int i) {
+                auto ld = [&](int i) {             // beyond the series the line still holds the previous transform: masked
                     const int e = 2 * i;
-                    return cplx{e < N ? (double)xs[(int64_t)e * ds] - mean : 0.0,
-                                e + 1 < N ? (double)xs[(int64_t)(e + 1) * ds] - mean : 0.0};
+                    const cplx r = buf[SK(i)];
+                    return cplx{e < N ? r.x - mean : 0.0, e + 1 < N ? r.y - mean : 0.0};
                 };
-                rf_pass_r<false, true, false>(plan.radix[ps], buf, M, plan.m[ps], WMt, ld, st_buf);
+                rf_pass_r<false, true, false>(s_rad[ps], buf, M, s_m[ps], WMt, ld, st_buf);
             } else {
-                rf_pass_r<false, false, false>(plan.radix[ps], buf, M, plan.m[ps], WMt, ld_buf, st_buf);
+                rf_pass_r<false, false, false>(s_rad[ps], buf, M, s_m[ps], WMt, ld_buf, st_buf);
             }
         }
         // ---- pointwise: power spectrum of the real series -> packed spectrum of its autocorrelation ----
@@ -489,7 +506,9 @@ k_acf_rfft(SeriesView v, RfftPlan plan, const cplx* __restrict__ WM, const cplx*
             } else {
                 // E = (Z[k] + conj Z[M-k]) / 2, O = (Z[k] - conj Z[M-k]) / 2i  (the factors 1/2 cancel in acf = r / r0)
                 const cplx E = cplx{a.x + b.x, a.y - b.y}, O = cplx{a.y + b.y, b.x - a.x};
-                const cplx w = WS[k];                                   // exp(-2 pi i k / S)
+                // exp(-2 pi i k / S) = w_M^(k >> 1) (w_S^1 if k is odd): from the shared-memory tables, no global load
+                cplx w = WMt.at(k >> 1, false);
+                if (k & 1) w = cmul(w, w_s1);
                 const cplx wo = cmul(w, O);
                 const cplx Xk = cadd(E, wo);                            // X[k]
                 const cplx Xm = cplx{E.x - wo.x, -(E.y - wo.y)};        // X[M-k] = conj(E - w O)
@@ -509,16 +528,16 @@ k_acf_rfft(SeriesView v, RfftPlan plan, const cplx* __restrict__ WM, const cplx*
         __syncthreads();
         // ---- inverse: digit-reversed -> natural; the last pass writes acf_2n, acf_2n+1 = z'_n / r0 ----
         const double sc = 1.0 / r0;
-        for (int ps = plan.n_pass - 1; ps >= 0; --ps) {
+        for (int ps = n_pass - 1; ps >= 0; --ps) {
             if (ps == 0) {
                 auto st_out = [&](int i, cplx val) {
                     const int e = 2 * i;
                     if (e < N) os[e] = val.x * sc;
                     if (e + 1 < N) os[e + 1] = val.y * sc;
                 };
-                rf_pass_r<true, false, true>(plan.radix[ps], buf, M, plan.m[ps], WMt, ld_buf, st_out);
+                rf_pass_r<true, false, true>(s_rad[ps], buf, M, s_m[ps], WMt, ld_buf, st_out);
             } else {
-                rf_pass_r<true, false, false>(plan.radix[ps], buf, M, plan.m[ps], WMt, ld_buf, st_buf);
+                rf_pass_r<true, false, false>(s_rad[ps], buf, M, s_m[ps], WMt, ld_buf, st_buf);
             }
         }
     }
@@ -621,7 +640,9 @@ int acf_fft_launch(const SeriesView& v, double* out, void* ws, size_t ws_bytes, 
         const RfftPlan plan = rfft_plan(M);
         k_rfft_twiddles<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(WM, WS, POS, plan, M);
         BK_LAUNCH_CHECK();
-        const size_t smem = (size_t)(M + M / 8 + 1) * sizeof(cplx);
+        size_t smem = (size_t)(M + M / 8 + 1) * sizeof(cplx);
+        const int pos_in_smem = smem + (size_t)M * sizeof(uint16_t) + 8 * 1024 <= 227 * 1024 ? 1 : 0;   // + static tables
+        if (pos_in_smem) smem += (size_t)M * sizeof(uint16_t);
         BK_CUDA(cudaFuncSetAttribute(k_acf_rfft<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         BK_CUDA(cudaFuncSetAttribute(k_acf_rfft<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int dev = 0, sms = 148;
@@ -629,8 +650,8 @@ int acf_fft_launch(const SeriesView& v, double* out, void* ws, size_t ws_bytes, 
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int per_sm = smem <= 100 * 1024 ? 2 : 1;
         const int64_t nb = v.n_series < (int64_t)sms * per_sm ? v.n_series : (int64_t)sms * per_sm;
-        if (v.dtype == BK_F64) k_acf_rfft<double><<<(unsigned)nb, RF_THREADS, smem, st>>>(v, plan, WM, WS, POS, out);
-        else k_acf_rfft<float><<<(unsigned)nb, RF_THREADS, smem, st>>>(v, plan, WM, WS, POS, out);
+        if (v.dtype == BK_F64) k_acf_rfft<double><<<(unsigned)nb, RF_THREADS, smem, st>>>(v, plan, WM, WS, POS, pos_in_smem, out);
+        else k_acf_rfft<float><<<(unsigned)nb, RF_THREADS, smem, st>>>(v, plan, WM, WS, POS, pos_in_smem, out);
         BK_LAUNCH_CHECK();
         return BK_OK;
     }
