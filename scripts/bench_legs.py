@@ -9,10 +9,22 @@ import torch.distributed as dist
 import bayes_kit_b200 as bk
 
 
-def _timed(fn, reps=5, warm=2):
+def _timed(fn, reps=5, warm=2, median=False):
+    """ms per call on the current stream; median=True times every call separately and returns the median (calls that
+    allocate hundreds of MB per invocation see an occasional caching-allocator stall that is not kernel time)."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    if median:
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
@@ -137,7 +149,7 @@ def leg_c5(hbm):
     ms_e = _timed(lambda: bk.ess(xs), reps=3, warm=1)
     ms_r = _timed(lambda: bk.rhat(x, draws_first=True), reps=3, warm=1)
     xa = xs[:8192]
-    ms_a = _timed(lambda: bk.autocorr(xa), reps=3, warm=1)
+    ms_a = _timed(lambda: bk.autocorr(xa), reps=7, warm=2, median=True)
     S = Cn * P
     return {"workload": f"c5 (reduced): {Cn} chains x {N} draws x {P} params fp32 in / fp64 accumulate",
             "ess": {"value": S / (ms_e * 1e-3), "unit": "series/s", "ms": ms_e,
