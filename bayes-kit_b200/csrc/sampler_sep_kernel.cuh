@@ -131,23 +131,29 @@ __global__ void __launch_bounds__(128) k_sep_sampler(SepArgs<T> a) {
                 if (a.L == 1) {
                     finish(xb, th);
                 } else {
-                    // x_s in xa, x_{s-1} in xb (no copy of the state: the first recurrence step reads th itself)
+                    // x_s in A, x_{s-1} in B: pair steps, then ONE single step, so that both parities of L run the
+                    // same tail (B = c A - B; finish(B, A)).  Odd L: the first recurrence step is peeled and reads th
+                    // itself (no copy of the state); even L: th is copied and the recurrence starts one step earlier.
+                    auto run = [&](T (&A_)[NE], T (&B_)[NE], int s) {
+                        for (; s + 2 < a.L; s += 2) {
 #pragma unroll
-                    for (int k = 0; k < NE; ++k) xa[k] = fmaf(c, xb[k], -th[k]);   // x_2
-                    int s = 2;
-                    for (; s + 1 < a.L; s += 2) {
-#pragma unroll
-                        for (int k = 0; k < NE; ++k) {
-                            xb[k] = fmaf(c, xa[k], -xb[k]);
-                            xa[k] = fmaf(c, xb[k], -xa[k]);
+                            for (int k = 0; k < NE; ++k) {
+                                B_[k] = fmaf(c, A_[k], -B_[k]);
+                                A_[k] = fmaf(c, B_[k], -A_[k]);
+                            }
                         }
-                    }
-                    if (s < a.L) {   // one recurrence step left: x_L lands in xb
 #pragma unroll
-                        for (int k = 0; k < NE; ++k) xb[k] = fmaf(c, xa[k], -xb[k]);
-                        finish(xb, xa);
+                        for (int k = 0; k < NE; ++k) B_[k] = fmaf(c, A_[k], -B_[k]);
+                        finish(B_, A_);
+                    };
+                    if (a.L & 1) {
+#pragma unroll
+                        for (int k = 0; k < NE; ++k) xa[k] = fmaf(c, xb[k], -th[k]);   // x_2
+                        run(xa, xb, 2);
                     } else {
-                        finish(xa, xb);
+#pragma unroll
+                        for (int k = 0; k < NE; ++k) xa[k] = th[k];
+                        run(xb, xa, 1);
                     }
                 }
             }
