@@ -104,6 +104,7 @@ k_hlr_tc(const __grid_constant__ CUtensorMap mapBeta, const __grid_constant__ CU
     const int64_t n_begin = split * a.rows_per_split;
     const int64_t n_end = n_begin + a.rows_per_split < a.N ? n_begin + a.rows_per_split : a.N;
     const int T = n_end > n_begin ? (int)((n_end - n_begin + NT - 1) / NT) : 0;
+    cudaTriggerProgrammaticLaunchCompletion();   // a dependent launch may be scheduled as SMs free up (it still waits for our completion)
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
@@ -120,10 +121,13 @@ k_hlr_tc(const __grid_constant__ CUtensorMap mapBeta, const __grid_constant__ CU
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_expect_tx(beta_full, 2 * ATOM);
-            tma_load_2d(sA1, &mapBeta, beta_full, 0, (int)c0);
-            tma_load_2d(sA1 + ATOM, &mapBeta, beta_full, 64, (int)c0);
-            for (int i = 0; i < T; ++i) {
+            // Programmatic dependent launch (the interior-step launches set the attribute): this grid may start
+            // while its predecessor in the stream (the finish kernel that writes the beta operand) is still
+            // running.  The X / y tiles do not depend on it -- the ring is filled first -- and only the operand
+            // load waits for the predecessor's completion.  Everything this kernel writes (part_g / part_ll) is
+            // written after MMAs that consumed the operand, i.e. after the wait.  Without the attribute the wait
+            // returns at once.
+            auto issue_x = [&](int i) {
                 const int s = i % NSTAGE;
                 const uint32_t ph = (uint32_t)(i / NSTAGE) & 1u;
                 const int n0 = (int)(n_begin + (int64_t)i * NT);
@@ -133,7 +137,14 @@ k_hlr_tc(const __grid_constant__ CUtensorMap mapBeta, const __grid_constant__ CU
                 tma_load_2d(st, &mapX, full(s), 0, n0);                 // X[n0.., j 0..63]
                 tma_load_2d(st + ATOM, &mapX, full(s), 64, n0);         // X[n0.., j 64..127]
                 bulk_load(st + 2 * ATOM, a.y + n0, NT * 4, full(s));
-            }
+            };
+            const int pre = T < NSTAGE ? T : NSTAGE;
+            for (int i = 0; i < pre; ++i) issue_x(i);
+            cudaGridDependencySynchronize();
+            mbar_expect_tx(beta_full, 2 * ATOM);
+            tma_load_2d(sA1, &mapBeta, beta_full, 0, (int)c0);
+            tma_load_2d(sA1 + ATOM, &mapBeta, beta_full, 64, (int)c0);
+            for (int i = pre; i < T; ++i) issue_x(i);
         }
     } else if (warp == 1) {
         if (lane == 0 && T > 0) {
@@ -496,6 +507,13 @@ size_t hlr_tc_eval_ws_bytes(const Model& m, int64_t C) {
            align_up((size_t)ns * C * 4, 256) + align_up(hlr_steps_cnt_words(C) * 4, 256) + 1024;
 }
 
+// BK_HLR_PDL=0 (diagnostic): plain stream-ordered launches for the interior leapfrog steps
+static bool hlr_pdl() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("BK_HLR_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+
 // one layout of the evaluation workspace for every entry point (the bf16 operand written by one call is read by the next)
 struct HlrWs {
     __nv_bfloat16 *bb, *bl;   // operand beta (hi, lo) [Cp, 128]
@@ -567,6 +585,17 @@ int hlr_tc_partial(const Model& m, const float* theta, int64_t C, void* ws, size
     prof_begin(BK_PROF_GRAD, st);
     if (mode == HLR_TC_LP) k_hlr_lp_tc<<<grid, THREADS, LP_SMEM_BYTES, st>>>(mB, mBl, mX, mXl, a);
     else if (a.need_ll) k_hlr_tc<true><<<grid, GTHREADS, SMEM_BYTES, st>>>(mB, mX, a);
+    else if (mode == HLR_TC_GRAD && hlr_pdl()) {
+        // interior-step gradient: programmatic dependent launch behind the finish kernel (see the producer warp)
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = grid; cfg.blockDim = dim3(GTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        BK_CUDA(cudaLaunchKernelEx(&cfg, k_hlr_tc<false>, mB, mX, a));
+    }
     else k_hlr_tc<false><<<grid, GTHREADS, SMEM_BYTES, st>>>(mB, mX, a);
     prof_end(BK_PROF_GRAD, st);
     BK_LAUNCH_CHECK();
@@ -646,6 +675,8 @@ __device__ __forceinline__ void hlr_finish_chain(float* __restrict__ th, float* 
 __global__ void k_hlr_finish_step(float* __restrict__ q, float* __restrict__ r, const float* __restrict__ part_g,
                                   int64_t C, int Dx, int D, int n_split, float eps, const float* __restrict__ metric,
                                   __nv_bfloat16* __restrict__ operand) {
+    cudaTriggerProgrammaticLaunchCompletion();   // the next gradient launch may start its prologue / X prefetch
+    cudaGridDependencySynchronize();             // the partial gradients of the launch before us are complete
     const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (c >= C) return;
@@ -924,7 +955,18 @@ int hlr_tc_interior_step(const Model& m, float* q, float* r, int64_t C, float ep
     int rc = hlr_tc_partial(m, q, C, ws, ws_bytes, &pg, &pl, &ns, st, HLR_TC_GRAD, operand_ready, &bb);
     if (rc) return rc;
     const int D = (int)m.d.dims;
-    k_hlr_finish_step<<<(unsigned)((C * 32 + 63) / 64), 64, 0, st>>>(q, r, pg, C, D - 2, D, ns, eps, metric, bb);
+    if (hlr_pdl()) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)((C * 32 + 63) / 64)); cfg.blockDim = dim3(64); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        BK_CUDA(cudaLaunchKernelEx(&cfg, k_hlr_finish_step, q, r, (const float*)pg, C, D - 2, D, ns, eps, metric, bb));
+    } else {
+        k_hlr_finish_step<<<(unsigned)((C * 32 + 63) / 64), 64, 0, st>>>(q, r, pg, C, D - 2, D, ns, eps, metric, bb);
+    }
     BK_LAUNCH_CHECK();
     return BK_OK;
 }

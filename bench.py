@@ -205,7 +205,7 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return run_reference_arm(args)
-    for v in ("BK_TC_DEBUG", "BK_DISABLE_TC", "BK_FORCE_GENERIC", "BK_HLR_DEBUG", "BK_ESS", "BK_ACF", "BK_LIB", "BK_TC_FUSE", "BK_TC_PAIR", "BK_SEP_WIDE", "BK_SMC_LAYOUT", "BK_SMC_OCC", "BK_ACF_RFFT", "BK_TC_TURN", "BK_HLR_FUSE", "BK_SEP_LAYOUT"):   # diagnostic switches of the library (for some of them "0" is the diagnostic value)
+    for v in ("BK_TC_DEBUG", "BK_DISABLE_TC", "BK_FORCE_GENERIC", "BK_HLR_DEBUG", "BK_ESS", "BK_ACF", "BK_LIB", "BK_TC_FUSE", "BK_TC_PAIR", "BK_SEP_WIDE", "BK_SMC_LAYOUT", "BK_SMC_OCC", "BK_ACF_RFFT", "BK_TC_TURN", "BK_HLR_FUSE", "BK_SEP_LAYOUT", "BK_HLR_PDL"):   # diagnostic switches of the library (for some of them "0" is the diagnostic value)
         if os.environ.get(v, "") != "":
             raise SystemExit(f"{v} is set: refusing to benchmark a diagnostic configuration")
 
