@@ -608,8 +608,8 @@ int hlr_tc_partial(const Model& m, const float* theta, int64_t C, void* ws, size
 // gradient), the leapfrog kick and drift  r += eps m g ; q += eps r  (hmc.py:48-49), and the bf16
 // operand (beta / 2, zero padded) of the NEXT gradient launch -- instead of three kernels
 // (finish, step, operand preparation) and two round trips of the gradient through HBM.
-// The partial sums of two dimensions per lane (up to 32 loads) are requested before any is consumed: inside the
-// multi-step kernel below this runs on the critical path of every leapfrog step.  Slices are summed in a fixed
+// The partial sums of all four dimensions of a lane (up to 64 loads) are requested before any is consumed: the finish
+// sits on the critical path of every leapfrog step.  Slices are summed in a fixed
 // order (four interleaved accumulators over the full groups of 4, the remainder into the first), independent of
 // which kernel calls it.
 __device__ __forceinline__ void hlr_finish_chain(float* __restrict__ th, float* __restrict__ rr,
@@ -620,45 +620,46 @@ __device__ __forceinline__ void hlr_finish_chain(float* __restrict__ th, float* 
     const float e2 = expf(-2.f * lam), ep2 = expf(2.f * lam);
     float sr = 0.f, ss = 0.f;
     const int ns4 = n_split & ~3;
+    constexpr int NJ = KJ / 32;                       // dimensions per lane (4)
+    float g[NJ][4];
+#pragma unroll
+    for (int h = 0; h < NJ; ++h) { g[h][0] = g[h][1] = g[h][2] = g[h][3] = 0.f; }
+    // all four dimensions of a lane travel together: 64 loads in flight per lane and chunk of 16 slices
 #pragma unroll 1
-    for (int jp = 0; jp < KJ / 64; ++jp) {
-        float g[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll 1
-        for (int s0 = 0; s0 < n_split; s0 += 16) {
-            float av[2][16];
+    for (int s0 = 0; s0 < n_split; s0 += 16) {
+        float av[NJ][16];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int j = lane + 32 * (2 * jp + h);
+        for (int h = 0; h < NJ; ++h) {
+            const int j = lane + 32 * h;
 #pragma unroll
-                for (int u = 0; u < 16; ++u)
-                    av[h][u] = (j < Dx && s0 + u < n_split) ? __ldcg(pg_chain + j + (int64_t)(s0 + u) * step) : 0.f;
-            }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    if (s0 + u < ns4) g[h][u & 3] += av[h][u];
-                    else if (s0 + u < n_split) g[h][0] += av[h][u];
-                }
-            }
+            for (int u = 0; u < 16; ++u)
+                av[h][u] = (j < Dx && s0 + u < n_split) ? __ldcg(pg_chain + j + (int64_t)(s0 + u) * step) : 0.f;
         }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int j = lane + 32 * (2 * jp + h);
-            float bq = 0.f;
-            if (j < Dx) {
-                const float d = th[j] - mu;
-                sr += d;
-                ss = fmaf(d, d, ss);
-                const float gs = ((g[h][0] + g[h][1]) + (g[h][2] + g[h][3])) - e2 * d;
-                const float rn = fmaf(eps * (metric ? metric[j] : 1.f), gs, rr[j]);
-                rr[j] = rn;
-                bq = fmaf(eps, rn, th[j]);
-                if (poison) bq = __int_as_float(0x7fc00000);
-                th[j] = bq;
+        for (int h = 0; h < NJ; ++h) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                if (s0 + u < ns4) g[h][u & 3] += av[h][u];
+                else if (s0 + u < n_split) g[h][0] += av[h][u];
             }
-            oprow[j] = __float2bfloat16_rn(0.5f * bq);
         }
+    }
+#pragma unroll
+    for (int h = 0; h < NJ; ++h) {
+        const int j = lane + 32 * h;
+        float bq = 0.f;
+        if (j < Dx) {
+            const float d = th[j] - mu;
+            sr += d;
+            ss = fmaf(d, d, ss);
+            const float gs = ((g[h][0] + g[h][1]) + (g[h][2] + g[h][3])) - e2 * d;
+            const float rn = fmaf(eps * (metric ? metric[j] : 1.f), gs, rr[j]);
+            rr[j] = rn;
+            bq = fmaf(eps, rn, th[j]);
+            if (poison) bq = __int_as_float(0x7fc00000);
+            th[j] = bq;
+        }
+        oprow[j] = __float2bfloat16_rn(0.5f * bq);
     }
     sr = warp_sum(sr);
     ss = warp_sum(ss);
